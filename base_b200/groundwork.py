@@ -1,0 +1,121 @@
+"""ctypes binding of libb9_groundwork.so (include/b9_groundwork.h).
+
+No fallback of any kind: if the library is missing this module raises on first
+use, and on a box without a CUDA device every compute call raises
+`GroundworkError` carrying the library's own message.  The CPU checker in
+`oracle/` is never imported from here.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+import numpy as np
+
+LIB_PATH = Path(__file__).resolve().parent / "libb9_groundwork.so"
+ABI_VERSION = 1
+DFMA_ILP, TRANS_ILP, THREADS = 8, 4, 256
+
+# every symbol include/b9_groundwork.h declares: name -> (restype, argtypes)
+_i, _ll, _d, _f = C.c_int, C.c_longlong, C.c_double, C.c_float
+_pd, _pi, _pll, _pf = C.POINTER(_d), C.POINTER(_i), C.POINTER(_ll), C.POINTER(_f)
+SYMBOLS = {
+    "b9gw_abi_version": (_i, []),
+    "b9gw_last_error": (C.c_char_p, []),
+    "b9gw_device_count": (_i, []),
+    "b9gw_device_info": (_i, [_i, _pi, _pi, _pll]),
+    "b9gw_dfma_peak": (_i, [_i, _i, _i, _d, _d, _i, _i, _pd, _pll, _pf, _pd]),
+    "b9gw_transcendental_rate": (_i, [_i, _i, _i, _i, _i, _i, _pd, _pll, _pf, _pd]),
+    "b9gw_map": (_i, [_i, _i, _pd, _pd, _ll]),
+    "b9gw_lse_rows": (_i, [_i, _pd, _ll, _ll, _i, _i, _pd, _pd, _pf]),
+}
+
+
+class GroundworkError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"libb9_groundwork error {code}: {msg}")
+        self.code = code
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise FileNotFoundError(
+                f"{LIB_PATH} is not built; run `python -c 'import __graft_entry__ as g; g.build()'`"
+                " (there is no CPU fallback)")
+        L = C.CDLL(str(LIB_PATH))
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(L, name)
+            fn.restype, fn.argtypes = res, args
+        if L.b9gw_abi_version() != ABI_VERSION:
+            raise RuntimeError("libb9_groundwork.so ABI version mismatch; rebuild")
+        _lib = L
+    return _lib
+
+
+def _ck(rc: int) -> None:
+    if rc != 0:
+        raise GroundworkError(rc, lib().b9gw_last_error().decode())
+
+
+def _ptr(a: np.ndarray | None):
+    return None if a is None else a.ctypes.data_as(_pd)
+
+
+def device_count() -> int:
+    return lib().b9gw_device_count()
+
+
+def device_info(device: int = 0) -> dict:
+    sm, mhz, l2 = _i(), _i(), _ll()
+    _ck(lib().b9gw_device_info(device, C.byref(sm), C.byref(mhz), C.byref(l2)))
+    return {"sm_count": sm.value, "sm_clock_mhz": mhz.value, "l2_bytes": l2.value}
+
+
+def dfma_peak(device=0, ctas_per_sm=8, iters=1 << 16, a=1.0 - 2.0 ** -12, b=2.0 ** -12,
+              warmup=3, reps=10, want_out=False) -> dict:
+    n, ms, tf = _ll(), _f(), _d()
+    out = None
+    if want_out:
+        out = np.empty(device_info(device)["sm_count"] * ctas_per_sm * THREADS, dtype=np.float64)
+    _ck(lib().b9gw_dfma_peak(device, ctas_per_sm, iters, a, b, warmup, reps, _ptr(out),
+                             C.byref(n), C.byref(ms), C.byref(tf)))
+    return {"n_threads": n.value, "ms_per_launch": ms.value, "tflops": tf.value, "out": out,
+            "iters": iters, "ctas_per_sm": ctas_per_sm, "launches": warmup + reps}
+
+
+def transcendental_rate(which: str, device=0, ctas_per_sm=8, iters=1 << 12, warmup=3, reps=10,
+                        want_out=False) -> dict:
+    w = {"exp": 0, "log": 1}[which]
+    n, ms, g = _ll(), _f(), _d()
+    out = None
+    if want_out:
+        out = np.empty(device_info(device)["sm_count"] * ctas_per_sm * THREADS, dtype=np.float64)
+    _ck(lib().b9gw_transcendental_rate(device, w, ctas_per_sm, iters, warmup, reps, _ptr(out),
+                                       C.byref(n), C.byref(ms), C.byref(g)))
+    return {"n_threads": n.value, "ms_per_launch": ms.value, "gevals_per_s": g.value, "out": out,
+            "iters": iters, "ctas_per_sm": ctas_per_sm, "launches": warmup + reps}
+
+
+def device_map(which: str, x: np.ndarray, device=0) -> np.ndarray:
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    y = np.empty_like(x)
+    _ck(lib().b9gw_map(device, {"exp": 0, "log": 1}[which], _ptr(x), _ptr(y), x.size))
+    return y
+
+
+def lse_rows(x: np.ndarray, device=0, warmup=0, reps=1) -> dict:
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    if x.ndim != 2:
+        raise ValueError("x must be rows x cols")
+    rows, cols = x.shape
+    row_lse = np.empty(rows, dtype=np.float64)
+    total, ms = _d(), _f()
+    _ck(lib().b9gw_lse_rows(device, _ptr(x), rows, cols, warmup, reps, _ptr(row_lse),
+                            C.byref(total), C.byref(ms)))
+    return {"row_lse": row_lse, "total": total.value, "ms_per_launch": ms.value,
+            "launches": 2 * (warmup + reps) if rows else (warmup + reps)}

@@ -1,0 +1,69 @@
+"""The CPU checker itself, pinned against exact arithmetic and scipy (no GPU)."""
+from fractions import Fraction
+
+import numpy as np
+import pytest
+from scipy.special import logsumexp
+
+from tests._ref import mixed_err
+
+
+def test_dfma_chain_is_correctly_rounded_fma(ref):
+    # fma(x,a,b) = round(x*a+b): replay in exact rationals, round once per step
+    a, b, iters = 1.0 - 2.0 ** -12, 2.0 ** -12, 64
+    got = ref.dfma_lanes(a, b, iters)
+    for lane in (0, 1, 17, 31):
+        xs = [1.0 + 0.125 * j + lane * 2.0 ** -10 for j in range(8)]
+        for _ in range(iters):
+            xs = [float(Fraction(x) * Fraction(a) + Fraction(b)) for x in xs]
+        s = xs[0]
+        for x in xs[1:]:
+            s += x
+        assert got[lane] == s
+
+
+def test_dfma_chain_converges_to_fixed_point(ref):
+    a, b = 1.0 - 2.0 ** -12, 2.0 ** -12          # x* = b/(1-a) = 1 per chain, 8 chains
+    assert np.allclose(ref.dfma_lanes(a, b, 1 << 17), 8.0, rtol=0, atol=1e-9)
+
+
+@pytest.mark.parametrize("cols", [1, 2, 31, 32, 33, 1000, 4096])
+def test_lse_orders_agree_with_scipy(ref, cols):
+    rng = np.random.default_rng(cols)
+    x = rng.normal(-50.0, 25.0, size=(64, cols))
+    want = logsumexp(x, axis=1)
+    for warp_order in (False, True):
+        got = ref.lse_rows(x, warp_order)
+        assert mixed_err(got, want) < 2e-14
+
+
+def test_lse_edge_cases(ref):
+    x = np.full((3, 40), -np.inf)
+    x[1, 5] = -700.0                 # a single finite term, far below exp's underflow
+    x[2, :] = 700.0                  # would overflow without the max shift
+    for warp_order in (False, True):
+        got = ref.lse_rows(x, warp_order)
+        assert got[0] == -np.inf
+        assert got[1] == -700.0
+        assert got[2] == pytest.approx(700.0 + np.log(40.0), rel=1e-15)
+    assert (ref.lse_rows(np.empty((4, 0)), True) == -np.inf).all()      # empty grid
+    assert ref.lse_rows(np.empty((0, 7)), True).size == 0               # no stars
+
+
+def test_reduction_order_effect_is_far_inside_1e_10(ref):
+    # SURVEY.md §7 "hard parts": how far can a warp-tree order move a result vs a serial loop?
+    rng = np.random.default_rng(0)
+    x = rng.normal(-40.0, 12.0, size=(2000, 1024))
+    s, w = ref.lse_rows(x, False), ref.lse_rows(x, True)
+    assert np.max(np.abs(s - w)) < 2e-14          # absolute: a few ulp of the row max (~40)
+    assert mixed_err(w, s) < 2e-14
+    # ...but NOT small relative to a row value that happens to sit near zero:
+    assert np.max(np.abs(s - w) / np.abs(s)) > 1e-13
+    tot_tree, tot_serial = ref.ordered_sum(s), ref.serial_sum(s)
+    assert abs(tot_tree - tot_serial) / abs(tot_serial) < 1e-13
+
+
+def test_ordered_sum_small_and_ragged(ref):
+    assert ref.ordered_sum(np.empty(0)) == 0.0
+    v = np.arange(1, 2050, dtype=np.float64)
+    assert ref.ordered_sum(v) == v.sum() == 2049 * 2050 / 2
