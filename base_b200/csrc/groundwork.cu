@@ -12,6 +12,7 @@
 // the lse kernels contain none on the value path.)
 
 #include <cuda_runtime.h>
+#include <chrono>
 #include <math.h>
 #include <stdio.h>
 #include <string.h>
@@ -85,7 +86,10 @@ trans_rate_kernel(double *__restrict__ out, int iters) {
     for (int i = 0; i < iters; ++i) {
 #pragma unroll
         for (int j = 0; j < B9GW_TRANS_ILP; ++j)
-            x[j] = (WHICH == 0) ? exp(-x[j]) : log(__dadd_rn(x[j], 3.0));
+            x[j] = (WHICH == 0)   ? exp(-x[j])
+                   : (WHICH == 1) ? log(__dadd_rn(x[j], 3.0))
+                   : (WHICH == 2) ? exp10(__dmul_rn(-0.4, x[j]))
+                                  : log10(__dadd_rn(x[j], 3.0));
     }
     double s = x[0];
 #pragma unroll
@@ -152,6 +156,8 @@ ordered_sum_kernel(const double *__restrict__ v, long long n, double *__restrict
     if (t == 0) *out = p[0];
 }
 
+__global__ void tick_kernel(double *out, double v) { *out = v; }
+
 struct Timer {
     cudaEvent_t a = nullptr, b = nullptr;
     cudaError_t init() {
@@ -215,7 +221,7 @@ done:
 
 extern "C" {
 
-int b9gw_abi_version(void) { return 1; }
+int b9gw_abi_version(void) { return 2; }
 
 const char *b9gw_last_error(void) { return g_err; }
 
@@ -263,22 +269,78 @@ int b9gw_transcendental_rate(int device, int which, int ctas_per_sm, int iters,
                              int warmup, int reps, double *out_host,
                              long long *n_threads, float *ms_per_launch,
                              double *gevals_per_s) {
-    if (which != 0 && which != 1) return fail(B9GW_E_ARG, "which must be 0 (exp) or 1 (log)");
+    if (which < 0 || which > 3) return fail(B9GW_E_ARG, "which must be 0 exp, 1 log, 2 exp10, 3 log10");
     long long nthr = 0;
     float ms = 0.f;
     int rc = run_chain_bench(
         device, ctas_per_sm, iters, warmup, reps, out_host, &nthr, &ms,
         [=](int grid, cudaStream_t st, double *out) {
-            if (which == 0)
-                trans_rate_kernel<0><<<grid, B9GW_DFMA_THREADS, 0, st>>>(out, iters);
-            else
-                trans_rate_kernel<1><<<grid, B9GW_DFMA_THREADS, 0, st>>>(out, iters);
+            switch (which) {
+                case 0: trans_rate_kernel<0><<<grid, B9GW_DFMA_THREADS, 0, st>>>(out, iters); break;
+                case 1: trans_rate_kernel<1><<<grid, B9GW_DFMA_THREADS, 0, st>>>(out, iters); break;
+                case 2: trans_rate_kernel<2><<<grid, B9GW_DFMA_THREADS, 0, st>>>(out, iters); break;
+                default: trans_rate_kernel<3><<<grid, B9GW_DFMA_THREADS, 0, st>>>(out, iters);
+            }
         });
     if (rc != B9GW_OK) return rc;
     if (n_threads) *n_threads = nthr;
     if (ms_per_launch) *ms_per_launch = ms;
     if (gevals_per_s)
         *gevals_per_s = (double)B9GW_TRANS_ILP * (double)iters * (double)nthr / (ms * 1e-3) * 1e-9;
+    return rc;
+}
+
+int b9gw_step_latency(int device, int warmup, int reps, float *us_launch_sync,
+                      float *us_launch_d2h_sync, float *us_graph_d2h_sync) {
+    using clk = std::chrono::steady_clock;
+    int rc = B9GW_OK;
+    double *d = nullptr, *h = nullptr;
+    cudaStream_t st = nullptr;
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    if (warmup < 0 || reps < 1) return fail(B9GW_E_ARG, "need warmup>=0, reps>=1");
+    if ((rc = select_device(device)) != B9GW_OK) return rc;
+    {
+        CK(cudaMalloc(&d, sizeof(double)));
+        CK(cudaMallocHost(&h, sizeof(double)));
+        CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        auto us = [&](clk::time_point a) {
+            return (float)(std::chrono::duration<double, std::micro>(clk::now() - a).count() / reps);
+        };
+        clk::time_point t0;
+        for (int i = 0; i < warmup + reps; ++i) {
+            if (i == warmup) t0 = clk::now();
+            tick_kernel<<<1, 1, 0, st>>>(d, (double)i);
+            CK(cudaStreamSynchronize(st));
+        }
+        if (us_launch_sync) *us_launch_sync = us(t0);
+        for (int i = 0; i < warmup + reps; ++i) {
+            if (i == warmup) t0 = clk::now();
+            tick_kernel<<<1, 1, 0, st>>>(d, (double)i);
+            CK(cudaMemcpyAsync(h, d, sizeof(double), cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            if (*h != (double)i) { rc = fail(B9GW_E_CUDA, "step_latency: stale read-back"); goto done; }
+        }
+        if (us_launch_d2h_sync) *us_launch_d2h_sync = us(t0);
+        CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+        tick_kernel<<<1, 1, 0, st>>>(d, -1.0);
+        CK(cudaMemcpyAsync(h, d, sizeof(double), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamEndCapture(st, &graph));
+        CK(cudaGraphInstantiate(&exec, graph, 0));
+        for (int i = 0; i < warmup + reps; ++i) {
+            if (i == warmup) t0 = clk::now();
+            CK(cudaGraphLaunch(exec, st));
+            CK(cudaStreamSynchronize(st));
+        }
+        if (us_graph_d2h_sync) *us_graph_d2h_sync = us(t0);
+        if (*h != -1.0) { rc = fail(B9GW_E_CUDA, "step_latency: graph read-back wrong"); goto done; }
+    }
+done:
+    if (exec) cudaGraphExecDestroy(exec);
+    if (graph) cudaGraphDestroy(graph);
+    if (st) cudaStreamDestroy(st);
+    if (h) cudaFreeHost(h);
+    if (d) cudaFree(d);
     return rc;
 }
 

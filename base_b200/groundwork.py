@@ -13,7 +13,7 @@ from pathlib import Path
 import numpy as np
 
 LIB_PATH = Path(__file__).resolve().parent / "libb9_groundwork.so"
-ABI_VERSION = 1
+ABI_VERSION = 2
 DFMA_ILP, TRANS_ILP, THREADS = 8, 4, 256
 
 # every symbol include/b9_groundwork.h declares: name -> (restype, argtypes)
@@ -26,6 +26,7 @@ SYMBOLS = {
     "b9gw_device_info": (_i, [_i, _pi, _pi, _pll]),
     "b9gw_dfma_peak": (_i, [_i, _i, _i, _d, _d, _i, _i, _pd, _pll, _pf, _pd]),
     "b9gw_transcendental_rate": (_i, [_i, _i, _i, _i, _i, _i, _pd, _pll, _pf, _pd]),
+    "b9gw_step_latency": (_i, [_i, _i, _i, _pf, _pf, _pf]),
     "b9gw_map": (_i, [_i, _i, _pd, _pd, _ll]),
     "b9gw_lse_rows": (_i, [_i, _pd, _ll, _ll, _i, _i, _pd, _pd, _pf]),
 }
@@ -90,7 +91,7 @@ def dfma_peak(device=0, ctas_per_sm=8, iters=1 << 16, a=1.0 - 2.0 ** -12, b=2.0 
 
 def transcendental_rate(which: str, device=0, ctas_per_sm=8, iters=1 << 12, warmup=3, reps=10,
                         want_out=False) -> dict:
-    w = {"exp": 0, "log": 1}[which]
+    w = {"exp": 0, "log": 1, "exp10": 2, "log10": 3}[which]
     n, ms, g = _ll(), _f(), _d()
     out = None
     if want_out:
@@ -99,6 +100,13 @@ def transcendental_rate(which: str, device=0, ctas_per_sm=8, iters=1 << 12, warm
                                        C.byref(n), C.byref(ms), C.byref(g)))
     return {"n_threads": n.value, "ms_per_launch": ms.value, "gevals_per_s": g.value, "out": out,
             "iters": iters, "ctas_per_sm": ctas_per_sm, "launches": warmup + reps}
+
+
+def step_latency(device=0, warmup=50, reps=2000) -> dict:
+    a, b, c = _f(), _f(), _f()
+    _ck(lib().b9gw_step_latency(device, warmup, reps, C.byref(a), C.byref(b), C.byref(c)))
+    return {"us_launch_sync": a.value, "us_launch_d2h_sync": b.value, "us_graph_d2h_sync": c.value,
+            "launches": 3 * (warmup + reps)}
 
 
 def device_map(which: str, x: np.ndarray, device=0) -> np.ndarray:

@@ -12,8 +12,8 @@ under the headline metric.
 What this run DOES measure, under the separate key `groundwork`, are the
 reference-independent denominators north_star demands before any roofline
 fraction can be quoted: the B200's FP64 DFMA peak (absent from
-MEASURED_PEAKS.json), FP64 exp/log rates, a fixed-order row log-sum-exp, and at
-N>1 the latency of the order-fixed cross-rank sum of 1024 per-chain scalars.
+MEASURED_PEAKS.json), FP64 exp/log/exp10/log10 rates, the host round trip of one
+dependent step, a fixed-order row log-sum-exp, and at N>1 the latency of the order-fixed cross-rank sum of 1024 per-chain scalars.
 A "step" here is one launch of the DFMA kernel; K steps are timed with CUDA
 events on the launching stream after W warm-up launches.  `gpu_launches` counts
 those groundwork kernels and nothing else.
@@ -159,7 +159,10 @@ def main() -> int:
         occ["64"] = round(r["tflops"], 3)
         e = gw.transcendental_rate("exp", local, iters=1 << 12, warmup=warmup, reps=args.steps)
         l = gw.transcendental_rate("log", local, iters=1 << 12, warmup=warmup, reps=args.steps)
-        launches += e["launches"] + l["launches"]
+        e10 = gw.transcendental_rate("exp10", local, iters=1 << 12, warmup=warmup, reps=max(3, args.steps // 4))
+        l10 = gw.transcendental_rate("log10", local, iters=1 << 12, warmup=warmup, reps=max(3, args.steps // 4))
+        lat = gw.step_latency(local, warmup=50, reps=2000)
+        launches += e["launches"] + l["launches"] + e10["launches"] + l10["launches"] + lat["launches"]
         rng = np.random.default_rng(1234)
         rows, cols = 10_000, 1_024  # 82 MB: under the 126 MB L2, second pass is an L2 hit
         x = rng.normal(-40.0, 12.0, size=(rows, cols))
@@ -173,6 +176,9 @@ def main() -> int:
         "dfma_tflops_by_warps_per_sm": occ,
         "fp64_exp_gevals_per_s": round(e["gevals_per_s"], 2),
         "fp64_log_gevals_per_s": round(l["gevals_per_s"], 2),
+        "fp64_exp10_gevals_per_s": round(e10["gevals_per_s"], 2),
+        "fp64_log10_gevals_per_s": round(l10["gevals_per_s"], 2),
+        "dependent_step_latency_us": {k: round(v, 2) for k, v in lat.items() if k.startswith("us_")},
         "lse_rows": {"rows": rows, "cols": cols, "ms_per_launch": round(s["ms_per_launch"], 4),
                      "gelem_per_s": round(rows * cols / (s["ms_per_launch"] * 1e-3) * 1e-9, 2),
                      "algorithmic_gb_per_s": round(rows * cols * 8 / (s["ms_per_launch"] * 1e-3) * 1e-9, 1)},

@@ -71,15 +71,27 @@ int b9gw_dfma_peak(int device, int ctas_per_sm, int iters, double a, double b,
                    long long *n_threads, float *ms_per_launch, double *tflops);
 
 /*
- * FP64 transcendental issue rate.  which = 0: x <- exp(-x); which = 1:
- * x <- log(x + 3).  Both are contractions, so the stored value is insensitive
- * to last-bit libm differences.  Same launch shape and timing as above with
+ * FP64 transcendental issue rate.  which = 0: x <- exp(-x); 1: x <- log(x + 3);
+ * 2: x <- exp10(-0.4 x) (magnitude -> flux); 3: x <- log10(x + 3).  All four
+ * are contractions, so the stored value is insensitive to last-bit libm
+ * differences.  Same launch shape and timing as above with
  * B9GW_TRANS_ILP chains per thread; gevals = 1e-9 * ILP*iters*n_threads / s.
  */
 int b9gw_transcendental_rate(int device, int which, int ctas_per_sm, int iters,
                              int warmup, int reps, double *out_host,
                              long long *n_threads, float *ms_per_launch,
                              double *gevals_per_s);
+
+/*
+ * Host round trip of one dependent step, the floor under a sequential MCMC
+ * chain: wall-clock microseconds per iteration, averaged over `reps`, of
+ *   us_launch_sync     : launch a 1-thread kernel, cudaStreamSynchronize
+ *   us_launch_d2h_sync : launch, cudaMemcpyAsync 8 B to pinned host, synchronize
+ *   us_graph_d2h_sync  : the same launch + copy replayed as one CUDA graph
+ * Timed on the host (std::chrono) because the host wait is what is measured.
+ */
+int b9gw_step_latency(int device, int warmup, int reps, float *us_launch_sync,
+                      float *us_launch_d2h_sync, float *us_graph_d2h_sync);
 
 /* Elementwise y[i] = exp(x[i]) (which=0) or log(x[i]) (which=1) on the device,
  * for comparing CUDA libm with the host's bit by bit. */

@@ -34,13 +34,16 @@ double b9ref_dfma_lane(int lane, double a, double b, int iters) {
     return s;
 }
 
-/* Same for b9gw_transcendental_rate (which = 0 exp(-x), 1 log(x+3)). */
+/* Same for b9gw_transcendental_rate (0 exp(-x), 1 log(x+3), 2 exp10(-0.4x), 3 log10(x+3)). */
 double b9ref_trans_lane(int lane, int which, int iters) {
     double x[ILP_TRANS];
     for (int j = 0; j < ILP_TRANS; ++j) x[j] = 0.5 + 0.25 * j + lane * 0x1p-8;
     for (int i = 0; i < iters; ++i)
         for (int j = 0; j < ILP_TRANS; ++j)
-            x[j] = which == 0 ? exp(-x[j]) : log(x[j] + 3.0);
+            x[j] = which == 0   ? exp(-x[j])
+                   : which == 1 ? log(x[j] + 3.0)
+                   : which == 2 ? pow(10.0, -0.4 * x[j])
+                                : log10(x[j] + 3.0);
     double s = x[0];
     for (int j = 1; j < ILP_TRANS; ++j) s += x[j];
     return s;

@@ -31,7 +31,7 @@ class Ref:
         return np.array([self.L.b9ref_dfma_lane(l, a, b, iters) for l in range(32)])
 
     def trans_lanes(self, which, iters):
-        w = {"exp": 0, "log": 1}[which]
+        w = {"exp": 0, "log": 1, "exp10": 2, "log10": 3}[which]
         return np.array([self.L.b9ref_trans_lane(l, w, iters) for l in range(32)])
 
     def map(self, which, x):

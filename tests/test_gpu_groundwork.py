@@ -49,7 +49,7 @@ def test_dfma_peak_is_plausible(gw):
     assert 5.0 < r["tflops"] < 45.0, r
 
 
-@pytest.mark.parametrize("which", ["exp", "log"])
+@pytest.mark.parametrize("which", ["exp", "log", "exp10", "log10"])
 def test_transcendental_chain(gw, ref, which):
     r = gw.transcendental_rate(which, 0, ctas_per_sm=1, iters=200, warmup=0, reps=1, want_out=True)
     want = ref.trans_lanes(which, 200)
@@ -71,6 +71,13 @@ def test_libm_distance_within_2_ulp(gw, ref, which):
     d = ulp_distance(got, want)
     assert d.max() <= 2, (d.max(), x[d.argmax()])
     print(f"\n{which}: bit-identical {np.mean(d == 0):.4%}, max {d.max()} ulp")
+
+
+def test_step_latency_is_measured_and_ordered(gw):
+    r = gw.step_latency(0, warmup=20, reps=300)
+    assert 1.0 < r["us_launch_sync"] < 500.0
+    assert r["us_launch_d2h_sync"] >= 0.8 * r["us_launch_sync"]
+    assert 1.0 < r["us_graph_d2h_sync"] < 500.0
 
 
 def test_map_empty(gw):
