@@ -11,7 +11,8 @@ from pathlib import Path
 
 PKG = Path(__file__).resolve().parent
 ROOT = PKG.parent
-CUDA_SRC = PKG / "csrc" / "groundwork.cu"
+CUDA_SRCS = tuple(PKG / "csrc" / n for n in ("groundwork.cu", "lse.cu", "vshard.cu"))
+CUDA_HDRS = (PKG / "csrc" / "common.cuh", ROOT / "include" / "b9_groundwork.h")
 CUDA_LIB = PKG / "libb9_groundwork.so"
 REF_SRC = ROOT / "oracle" / "groundwork_ref.c"
 REF_LIB = ROOT / "oracle" / "libb9_groundwork_ref.so"
@@ -32,10 +33,9 @@ def _run(cmd):
 
 
 def build_cuda(force: bool = False) -> Path:
-    header = ROOT / "include" / "b9_groundwork.h"
-    if force or _stale(CUDA_LIB, CUDA_SRC, header):
+    if force or _stale(CUDA_LIB, *CUDA_SRCS, *CUDA_HDRS):
         nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-        _run([nvcc, *NVCC_FLAGS, f"-I{ROOT / 'include'}", "-o", CUDA_LIB, CUDA_SRC])
+        _run([nvcc, *NVCC_FLAGS, f"-I{ROOT / 'include'}", "-o", CUDA_LIB, *CUDA_SRCS])
     return CUDA_LIB
 
 

@@ -1,54 +1,35 @@
-// groundwork.cu — reference-independent FP64 groundwork kernels for sm_100a.
+// groundwork.cu — reference-independent FP64 rate and latency probes for sm_100a.
 //
 // The BASE-9 hot path is BLOCKED: /root/reference/README.md:1-4 is a
 // relocation notice and no base-cpp source is staged.  Nothing here restates or
 // imitates reference code.  These kernels measure what north_star requires
 // before a roofline fraction can be quoted for an FP64 likelihood on B200:
-// the DFMA peak, exp/log rates, CUDA-libm vs host-libm distance, and how a
-// fixed-order warp log-sum-exp compares with a serial CPU one.
+// the DFMA peak, exp/log/exp10/log10 rates (on one argument and on a spread),
+// CUDA-libm vs host-libm distance, and the host round trip of a dependent step.
+// The fixed-order log-sum-exp lives in lse.cu, the cross-rank sum in vshard.cu.
 //
-// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -fmad=true
-// (FMA is explicit via fma(); --fmad only affects a*b+c the compiler finds, and
-// the lse kernels contain none on the value path.)
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3
+// (FMA is explicit via fma(); value paths use __dadd_rn/__dmul_rn, which -fmad
+// never contracts.)
 
-#include <cuda_runtime.h>
 #include <chrono>
 #include <math.h>
-#include <stdio.h>
 #include <string.h>
 
-#include "b9_groundwork.h"
+#include "common.cuh"
+
+namespace b9gw {
+char *err_buf() {
+    thread_local char buf[kErrBytes] = "";
+    return buf;
+}
+}  // namespace b9gw
 
 namespace {
 
-thread_local char g_err[512] = "";
-
-int fail(int code, const char *what, cudaError_t e = cudaSuccess) {
-    if (e != cudaSuccess)
-        snprintf(g_err, sizeof g_err, "%s: %s", what, cudaGetErrorString(e));
-    else
-        snprintf(g_err, sizeof g_err, "%s", what);
-    return code;
-}
-
-#define CK(call)                                                   \
-    do {                                                           \
-        cudaError_t e_ = (call);                                   \
-        if (e_ != cudaSuccess) { rc = fail(B9GW_E_CUDA, #call, e_); goto done; } \
-    } while (0)
-
-int select_device(int device) {
-    int n = 0;
-    cudaError_t e = cudaGetDeviceCount(&n);
-    if (e != cudaSuccess || n == 0) {
-        cudaGetLastError();
-        return fail(B9GW_E_NODEVICE, "no CUDA device visible (no CPU fallback exists)");
-    }
-    if (device < 0 || device >= n) return fail(B9GW_E_ARG, "device index out of range");
-    e = cudaSetDevice(device);
-    if (e != cudaSuccess) return fail(B9GW_E_CUDA, "cudaSetDevice", e);
-    return B9GW_OK;
-}
+using b9gw::fail;
+using b9gw::sm_count_of;
+using b9gw::Timer;
 
 // ---------------------------------------------------------------- DFMA peak
 // Each thread: ILP independent chains, fully unrolled; a and b arrive as kernel
@@ -74,6 +55,8 @@ dfma_peak_kernel(double *__restrict__ out, double a, double b, int iters) {
 }
 
 // ------------------------------------------------------- exp / log chain rate
+// WHICH 0..3 are contractions: after a few dozen iterations each thread sits at
+// the map's fixed point, so the rate is a single-argument, mid-range rate.
 template <int WHICH>
 __global__ void __launch_bounds__(B9GW_DFMA_THREADS)
 trans_rate_kernel(double *__restrict__ out, int iters) {
@@ -97,86 +80,54 @@ trans_rate_kernel(double *__restrict__ out, int iters) {
     out[t] = s;
 }
 
+// A fresh argument per evaluation, assembled on the integer pipe: sign, one of
+// 16 consecutive binary exponents starting at 2^e_lo, and 20 mantissa bits from
+// a 32-bit LCG.  The only FP64 work besides the function is one DADD.
+__device__ __forceinline__ double spread_arg(unsigned &state, int e_lo, unsigned sign) {
+    state = state * 1664525u + 1013904223u;
+    const unsigned e = (unsigned)(1023 + e_lo) + (state >> 28);
+    return __hiloint2double((int)(sign | (e << 20) | ((state >> 8) & 0xFFFFFu)), 0);
+}
+
+template <int WHICH>   // 4: exp(-(2^[-6,9] * 1.f)),  5: log(2^[-8,7] * 1.f)
+__global__ void __launch_bounds__(B9GW_DFMA_THREADS)
+spread_rate_kernel(double *__restrict__ out, int iters) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    unsigned st[B9GW_TRANS_ILP];
+    double acc[B9GW_TRANS_ILP];
+#pragma unroll
+    for (int j = 0; j < B9GW_TRANS_ILP; ++j) {
+        st[j] = (unsigned)(lane * B9GW_TRANS_ILP + j) * 2654435761u + 12345u;
+        acc[j] = 0.0;
+    }
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int j = 0; j < B9GW_TRANS_ILP; ++j) {
+            const double v = (WHICH == 4) ? exp(spread_arg(st[j], -6, 0x80000000u))
+                                          : log(spread_arg(st[j], -8, 0u));
+            acc[j] = __dadd_rn(acc[j], v);
+        }
+    }
+    double s = acc[0];
+#pragma unroll
+    for (int j = 1; j < B9GW_TRANS_ILP; ++j) s = __dadd_rn(s, acc[j]);
+    out[t] = s;
+}
+
 template <int WHICH>
 __global__ void map_kernel(const double *__restrict__ x, double *__restrict__ y,
                            long long n) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long stride = (long long)gridDim.x * blockDim.x;
-    for (; i < n; i += stride) y[i] = (WHICH == 0) ? exp(x[i]) : log(x[i]);
-}
-
-// ------------------------------------------------------ fixed-order row LSE
-// One warp per row, 8 rows per CTA.  Lane-strided reads are 256-byte coalesced
-// segments.  The second pass re-reads the row; for the row lengths of interest
-// (<= a few thousand columns) that is an L1/L2 hit, not HBM traffic.
-constexpr int LSE_WARPS = 8;
-
-__global__ void __launch_bounds__(LSE_WARPS * 32)
-lse_rows_kernel(const double *__restrict__ x, long long rows, long long cols,
-                double *__restrict__ row_lse) {
-    const int lane = threadIdx.x & 31;
-    const long long row = (long long)blockIdx.x * LSE_WARPS + (threadIdx.x >> 5);
-    if (row >= rows) return;  // whole warp exits together
-    const double *xr = x + row * cols;
-
-    double m = -INFINITY;
-    for (long long c = lane; c < cols; c += 32) m = fmax(m, xr[c]);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
-
-    double r;
-    if (m == -INFINITY) {
-        r = -INFINITY;  // every term is exp(-inf) = 0 (also covers cols == 0)
-    } else {
-        double s = 0.0;
-        for (long long c = lane; c < cols; c += 32)
-            s = __dadd_rn(s, exp(__dsub_rn(xr[c], m)));
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1)
-            s = __dadd_rn(s, __shfl_xor_sync(0xffffffffu, s, o));
-        r = __dadd_rn(m, log(s));
-    }
-    if (lane == 0) row_lse[row] = r;
-}
-
-// Fixed-order sum of n doubles: 1024 strided serial partials, then a pairwise
-// tree in shared memory.  One CTA; the order is a function of n alone.
-__global__ void __launch_bounds__(1024)
-ordered_sum_kernel(const double *__restrict__ v, long long n, double *__restrict__ out) {
-    __shared__ double p[1024];
-    const int t = threadIdx.x;
-    double s = 0.0;
-    for (long long i = t; i < n; i += 1024) s = __dadd_rn(s, v[i]);
-    p[t] = s;
-    __syncthreads();
-    for (int w = 512; w > 0; w >>= 1) {
-        if (t < w) p[t] = __dadd_rn(p[t], p[t + w]);
-        __syncthreads();
-    }
-    if (t == 0) *out = p[0];
+    for (; i < n; i += stride)
+        y[i] = (WHICH == 0) ? exp(x[i]) : (WHICH == 1) ? log(x[i])
+               : (WHICH == 2) ? exp10(x[i]) : log10(x[i]);
 }
 
 __global__ void tick_kernel(double *out, double v) { *out = v; }
 
-struct Timer {
-    cudaEvent_t a = nullptr, b = nullptr;
-    cudaError_t init() {
-        cudaError_t e = cudaEventCreate(&a);
-        return e != cudaSuccess ? e : cudaEventCreate(&b);
-    }
-    ~Timer() {
-        if (a) cudaEventDestroy(a);
-        if (b) cudaEventDestroy(b);
-    }
-};
-
-int sm_count_of(int device, int *sms) {
-    cudaError_t e = cudaDeviceGetAttribute(sms, cudaDevAttrMultiProcessorCount, device);
-    if (e != cudaSuccess) return fail(B9GW_E_CUDA, "cudaDeviceGetAttribute(SM count)", e);
-    return B9GW_OK;
-}
-
-// Shared body of the two chain benchmarks: launch(grid, stream) runs one launch.
+// Shared body of the chain benchmarks: launch(grid, stream, out) runs one launch.
 template <class Launch>
 int run_chain_bench(int device, int ctas_per_sm, int iters, int warmup, int reps,
                     double *out_host, long long *n_threads, float *ms_per_launch,
@@ -189,7 +140,8 @@ int run_chain_bench(int device, int ctas_per_sm, int iters, int warmup, int reps
     long long nthr = 0;
     if (ctas_per_sm < 1 || ctas_per_sm > 32 || iters < 1 || warmup < 0 || reps < 1)
         return fail(B9GW_E_ARG, "need 1<=ctas_per_sm<=32, iters>=1, warmup>=0, reps>=1");
-    if ((rc = select_device(device)) != B9GW_OK) return rc;
+    b9gw::DeviceGuard guard(device);
+    if (guard.rc() != B9GW_OK) return guard.rc();
     if ((rc = sm_count_of(device, &sms)) != B9GW_OK) return rc;
     {
         const int grid = sms * ctas_per_sm;
@@ -221,9 +173,9 @@ done:
 
 extern "C" {
 
-int b9gw_abi_version(void) { return 2; }
+int b9gw_abi_version(void) { return 3; }
 
-const char *b9gw_last_error(void) { return g_err; }
+const char *b9gw_last_error(void) { return b9gw::err_buf(); }
 
 int b9gw_device_count(void) {
     int n = 0;
@@ -235,9 +187,9 @@ int b9gw_device_count(void) {
 }
 
 int b9gw_device_info(int device, int *sm_count, int *sm_clock_mhz, long long *l2_bytes) {
-    int rc = select_device(device);
-    if (rc != B9GW_OK) return rc;
-    int v = 0;
+    int rc = B9GW_OK, v = 0;
+    b9gw::DeviceGuard guard(device);
+    if (guard.rc() != B9GW_OK) return guard.rc();
     CK(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device));
     if (sm_count) *sm_count = v;
     CK(cudaDeviceGetAttribute(&v, cudaDevAttrClockRate, device));
@@ -269,17 +221,21 @@ int b9gw_transcendental_rate(int device, int which, int ctas_per_sm, int iters,
                              int warmup, int reps, double *out_host,
                              long long *n_threads, float *ms_per_launch,
                              double *gevals_per_s) {
-    if (which < 0 || which > 3) return fail(B9GW_E_ARG, "which must be 0 exp, 1 log, 2 exp10, 3 log10");
+    if (which < 0 || which > 5)
+        return fail(B9GW_E_ARG, "which must be 0 exp, 1 log, 2 exp10, 3 log10, 4 exp-spread, 5 log-spread");
     long long nthr = 0;
     float ms = 0.f;
     int rc = run_chain_bench(
         device, ctas_per_sm, iters, warmup, reps, out_host, &nthr, &ms,
         [=](int grid, cudaStream_t st, double *out) {
+            constexpr int T = B9GW_DFMA_THREADS;
             switch (which) {
-                case 0: trans_rate_kernel<0><<<grid, B9GW_DFMA_THREADS, 0, st>>>(out, iters); break;
-                case 1: trans_rate_kernel<1><<<grid, B9GW_DFMA_THREADS, 0, st>>>(out, iters); break;
-                case 2: trans_rate_kernel<2><<<grid, B9GW_DFMA_THREADS, 0, st>>>(out, iters); break;
-                default: trans_rate_kernel<3><<<grid, B9GW_DFMA_THREADS, 0, st>>>(out, iters);
+                case 0: trans_rate_kernel<0><<<grid, T, 0, st>>>(out, iters); break;
+                case 1: trans_rate_kernel<1><<<grid, T, 0, st>>>(out, iters); break;
+                case 2: trans_rate_kernel<2><<<grid, T, 0, st>>>(out, iters); break;
+                case 3: trans_rate_kernel<3><<<grid, T, 0, st>>>(out, iters); break;
+                case 4: spread_rate_kernel<4><<<grid, T, 0, st>>>(out, iters); break;
+                default: spread_rate_kernel<5><<<grid, T, 0, st>>>(out, iters);
             }
         });
     if (rc != B9GW_OK) return rc;
@@ -298,8 +254,10 @@ int b9gw_step_latency(int device, int warmup, int reps, float *us_launch_sync,
     cudaStream_t st = nullptr;
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t exec = nullptr;
+    bool capturing = false;
     if (warmup < 0 || reps < 1) return fail(B9GW_E_ARG, "need warmup>=0, reps>=1");
-    if ((rc = select_device(device)) != B9GW_OK) return rc;
+    b9gw::DeviceGuard guard(device);
+    if (guard.rc() != B9GW_OK) return guard.rc();
     {
         CK(cudaMalloc(&d, sizeof(double)));
         CK(cudaMallocHost(&h, sizeof(double)));
@@ -323,8 +281,10 @@ int b9gw_step_latency(int device, int warmup, int reps, float *us_launch_sync,
         }
         if (us_launch_d2h_sync) *us_launch_d2h_sync = us(t0);
         CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+        capturing = true;
         tick_kernel<<<1, 1, 0, st>>>(d, -1.0);
         CK(cudaMemcpyAsync(h, d, sizeof(double), cudaMemcpyDeviceToHost, st));
+        capturing = false;                 // EndCapture ends it whether or not it succeeds
         CK(cudaStreamEndCapture(st, &graph));
         CK(cudaGraphInstantiate(&exec, graph, 0));
         for (int i = 0; i < warmup + reps; ++i) {
@@ -336,6 +296,12 @@ int b9gw_step_latency(int device, int warmup, int reps, float *us_launch_sync,
         if (*h != -1.0) { rc = fail(B9GW_E_CUDA, "step_latency: graph read-back wrong"); goto done; }
     }
 done:
+    if (capturing) {                       // a call failed mid-capture: do not destroy a capturing stream
+        cudaGraph_t dead = nullptr;
+        cudaStreamEndCapture(st, &dead);
+        if (dead) cudaGraphDestroy(dead);
+        cudaGetLastError();
+    }
     if (exec) cudaGraphExecDestroy(exec);
     if (graph) cudaGraphDestroy(graph);
     if (st) cudaStreamDestroy(st);
@@ -347,72 +313,27 @@ done:
 int b9gw_map(int device, int which, const double *x_host, double *y_host, long long n) {
     int rc = B9GW_OK, sms = 0;
     double *dx = nullptr, *dy = nullptr;
-    if (which != 0 && which != 1) return fail(B9GW_E_ARG, "which must be 0 (exp) or 1 (log)");
-    if (n < 0 || (n > 0 && (!x_host || !y_host))) return fail(B9GW_E_ARG, "null buffer or n<0");
-    if ((rc = select_device(device)) != B9GW_OK) return rc;
+    if (which < 0 || which > 3) return fail(B9GW_E_ARG, "which must be 0 exp, 1 log, 2 exp10, 3 log10");
+    if (!b9gw::count_ok(n) || (n > 0 && (!x_host || !y_host)))
+        return fail(B9GW_E_ARG, "null buffer, n<0 or n*8 overflows");
+    b9gw::DeviceGuard guard(device);
+    if (guard.rc() != B9GW_OK) return guard.rc();
     if (n == 0) return B9GW_OK;
     if ((rc = sm_count_of(device, &sms)) != B9GW_OK) return rc;
     CK(cudaMalloc(&dx, n * sizeof(double)));
     CK(cudaMalloc(&dy, n * sizeof(double)));
     CK(cudaMemcpy(dx, x_host, n * sizeof(double), cudaMemcpyHostToDevice));
-    if (which == 0)
-        map_kernel<0><<<sms * 8, 256>>>(dx, dy, n);
-    else
-        map_kernel<1><<<sms * 8, 256>>>(dx, dy, n);
+    switch (which) {
+        case 0: map_kernel<0><<<sms * 8, 256>>>(dx, dy, n); break;
+        case 1: map_kernel<1><<<sms * 8, 256>>>(dx, dy, n); break;
+        case 2: map_kernel<2><<<sms * 8, 256>>>(dx, dy, n); break;
+        default: map_kernel<3><<<sms * 8, 256>>>(dx, dy, n);
+    }
     CK(cudaGetLastError());
     CK(cudaMemcpy(y_host, dy, n * sizeof(double), cudaMemcpyDeviceToHost));
 done:
     if (dx) cudaFree(dx);
     if (dy) cudaFree(dy);
-    return rc;
-}
-
-int b9gw_lse_rows(int device, const double *x_host, long long rows, long long cols,
-                  int warmup, int reps, double *row_lse_host, double *total_host,
-                  float *ms_per_launch) {
-    int rc = B9GW_OK;
-    double *dx = nullptr, *dr = nullptr, *dt = nullptr;
-    cudaStream_t st = nullptr;
-    Timer tm;
-    float ms = 0.f;
-    if (rows < 0 || cols < 0 || warmup < 0 || reps < 1)
-        return fail(B9GW_E_ARG, "need rows>=0, cols>=0, warmup>=0, reps>=1");
-    if (rows * cols > 0 && !x_host) return fail(B9GW_E_ARG, "x_host is null");
-    if (!total_host) return fail(B9GW_E_ARG, "total_host is null");
-    if ((rows + LSE_WARPS - 1) / LSE_WARPS > 0x7fffffffLL) return fail(B9GW_E_ARG, "too many rows");
-    if ((rc = select_device(device)) != B9GW_OK) return rc;
-    {
-        const long long n = rows * cols;
-        const unsigned grid = (unsigned)((rows + LSE_WARPS - 1) / LSE_WARPS);
-        CK(cudaMalloc(&dx, (n > 0 ? n : 1) * sizeof(double)));
-        CK(cudaMalloc(&dr, (rows > 0 ? rows : 1) * sizeof(double)));
-        CK(cudaMalloc(&dt, sizeof(double)));
-        if (n > 0) CK(cudaMemcpy(dx, x_host, n * sizeof(double), cudaMemcpyHostToDevice));
-        CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-        CK(tm.init());
-        for (int i = 0; i < warmup + reps; ++i) {
-            if (i == warmup) {
-                CK(cudaStreamSynchronize(st));
-                CK(cudaEventRecord(tm.a, st));
-            }
-            if (grid > 0)
-                lse_rows_kernel<<<grid, LSE_WARPS * 32, 0, st>>>(dx, rows, cols, dr);
-            ordered_sum_kernel<<<1, 1024, 0, st>>>(dr, rows, dt);
-        }
-        CK(cudaEventRecord(tm.b, st));
-        CK(cudaGetLastError());
-        CK(cudaStreamSynchronize(st));
-        CK(cudaEventElapsedTime(&ms, tm.a, tm.b));
-        if (row_lse_host && rows > 0)
-            CK(cudaMemcpy(row_lse_host, dr, rows * sizeof(double), cudaMemcpyDeviceToHost));
-        CK(cudaMemcpy(total_host, dt, sizeof(double), cudaMemcpyDeviceToHost));
-    }
-    if (ms_per_launch) *ms_per_launch = ms / reps;
-done:
-    if (st) cudaStreamDestroy(st);
-    if (dx) cudaFree(dx);
-    if (dr) cudaFree(dr);
-    if (dt) cudaFree(dt);
     return rc;
 }
 

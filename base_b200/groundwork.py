@@ -13,12 +13,15 @@ from pathlib import Path
 import numpy as np
 
 LIB_PATH = Path(__file__).resolve().parent / "libb9_groundwork.so"
-ABI_VERSION = 2
+ABI_VERSION = 3
 DFMA_ILP, TRANS_ILP, THREADS = 8, 4, 256
+LSE_REG_COLS, MAX_WORLD, MAX_VSHARDS, IPC_HANDLE_BYTES = 1024, 16, 128, 64
+E_NODEVICE, E_CUDA, E_ARG, E_TIMEOUT, E_STATE = -1, -2, -3, -4, -5
 
 # every symbol include/b9_groundwork.h declares: name -> (restype, argtypes)
 _i, _ll, _d, _f = C.c_int, C.c_longlong, C.c_double, C.c_float
 _pd, _pi, _pll, _pf = C.POINTER(_d), C.POINTER(_i), C.POINTER(_ll), C.POINTER(_f)
+_vp, _ull = C.c_void_p, C.c_ulonglong
 SYMBOLS = {
     "b9gw_abi_version": (_i, []),
     "b9gw_last_error": (C.c_char_p, []),
@@ -29,6 +32,19 @@ SYMBOLS = {
     "b9gw_step_latency": (_i, [_i, _i, _i, _pf, _pf, _pf]),
     "b9gw_map": (_i, [_i, _i, _pd, _pd, _ll]),
     "b9gw_lse_rows": (_i, [_i, _pd, _ll, _ll, _i, _i, _pd, _pd, _pf]),
+    "b9gw_generate_terms": (_i, [_i, _ll, _ll, _pd]),
+    "b9gw_lse_generated": (_i, [_i, _ll, _ll, _i, _i, _pd, _pd, _pf]),
+    "b9gw_vshard_bounds": (_i, [_ll, _i, _i, _pll, _pll]),
+    # *_dev arguments are raw device addresses (c_void_p), e.g. torch.Tensor.data_ptr()
+    "b9gw_shard_partials": (_i, [_vp, _ll, _ll, _ll, _i, _i, _i, _vp, _vp]),
+    "b9gw_comm_create": (_i, [_i, _i, _i, _i, _ll, C.POINTER(_vp), _vp]),
+    "b9gw_comm_connect": (_i, [_vp, _vp]),
+    "b9gw_ordered_allreduce": (_i, [_vp, _vp, _vp, _ll, _vp]),
+    "b9gw_comm_set_timeout_ms": (_i, [_vp, _i]),
+    "b9gw_comm_status": (_i, [_vp, _pi, C.POINTER(_ull)]),
+    "b9gw_allreduce_latency": (_i, [_vp, _ll, _i, _i, _pf, _pf]),
+    "b9gw_comm_destroy": (_i, [_vp]),
+    "b9gw_vshard_total": (_i, [_i, _pd, _ll, _ll, _i, _pd, _pd]),
 }
 
 
@@ -89,9 +105,13 @@ def dfma_peak(device=0, ctas_per_sm=8, iters=1 << 16, a=1.0 - 2.0 ** -12, b=2.0 
             "iters": iters, "ctas_per_sm": ctas_per_sm, "launches": warmup + reps}
 
 
+TRANS_WHICH = {"exp": 0, "log": 1, "exp10": 2, "log10": 3, "exp_spread": 4, "log_spread": 5}
+MAP_WHICH = {"exp": 0, "log": 1, "exp10": 2, "log10": 3}
+
+
 def transcendental_rate(which: str, device=0, ctas_per_sm=8, iters=1 << 12, warmup=3, reps=10,
                         want_out=False) -> dict:
-    w = {"exp": 0, "log": 1, "exp10": 2, "log10": 3}[which]
+    w = TRANS_WHICH[which]
     n, ms, g = _ll(), _f(), _d()
     out = None
     if want_out:
@@ -112,7 +132,7 @@ def step_latency(device=0, warmup=50, reps=2000) -> dict:
 def device_map(which: str, x: np.ndarray, device=0) -> np.ndarray:
     x = np.ascontiguousarray(x, dtype=np.float64)
     y = np.empty_like(x)
-    _ck(lib().b9gw_map(device, {"exp": 0, "log": 1}[which], _ptr(x), _ptr(y), x.size))
+    _ck(lib().b9gw_map(device, MAP_WHICH[which], _ptr(x), _ptr(y), x.size))
     return y
 
 
@@ -126,4 +146,38 @@ def lse_rows(x: np.ndarray, device=0, warmup=0, reps=1) -> dict:
     _ck(lib().b9gw_lse_rows(device, _ptr(x), rows, cols, warmup, reps, _ptr(row_lse),
                             C.byref(total), C.byref(ms)))
     return {"row_lse": row_lse, "total": total.value, "ms_per_launch": ms.value,
-            "launches": 2 * (warmup + reps) if rows else (warmup + reps)}
+            "launches": warmup + reps}
+
+
+def generate_terms(rows: int, cols: int, device=0) -> np.ndarray:
+    x = np.empty((rows, cols), dtype=np.float64)
+    _ck(lib().b9gw_generate_terms(device, rows, cols, _ptr(x)))
+    return x
+
+
+def lse_generated(rows: int, cols: int, device=0, warmup=0, reps=1) -> dict:
+    row_lse = np.empty(rows, dtype=np.float64)
+    total, ms = _d(), _f()
+    _ck(lib().b9gw_lse_generated(device, rows, cols, warmup, reps, _ptr(row_lse), C.byref(total),
+                                 C.byref(ms)))
+    return {"row_lse": row_lse, "total": total.value, "ms_per_launch": ms.value,
+            "launches": warmup + reps}
+
+
+def vshard_bounds(n_stars: int, n_vshards: int, shard: int) -> tuple[int, int]:
+    lo, hi = _ll(), _ll()
+    _ck(lib().b9gw_vshard_bounds(n_stars, n_vshards, shard, C.byref(lo), C.byref(hi)))
+    return lo.value, hi.value
+
+
+def vshard_total(values: np.ndarray, n_vshards: int, device=0) -> dict:
+    """World = 1, host buffers: per-shard partials [V, chains] and total [chains]."""
+    values = np.ascontiguousarray(values, dtype=np.float64)
+    if values.ndim != 2:
+        raise ValueError("values must be chains x stars")
+    chains, n = values.shape
+    partials = np.empty((n_vshards, chains), dtype=np.float64)
+    total = np.empty(chains, dtype=np.float64)
+    _ck(lib().b9gw_vshard_total(device, _ptr(values), chains, n, n_vshards, _ptr(partials),
+                                _ptr(total)))
+    return {"partials": partials, "total": total}

@@ -13,10 +13,12 @@ What this run DOES measure, under the separate key `groundwork`, are the
 reference-independent denominators north_star demands before any roofline
 fraction can be quoted: the B200's FP64 DFMA peak (absent from
 MEASURED_PEAKS.json), FP64 exp/log/exp10/log10 rates, the host round trip of one
-dependent step, a fixed-order row log-sum-exp, and at N>1 the latency of the order-fixed cross-rank sum of 1024 per-chain scalars.
-A "step" here is one launch of the DFMA kernel; K steps are timed with CUDA
-events on the launching stream after W warm-up launches.  `gpu_launches` counts
-those groundwork kernels and nothing else.
+dependent step, a fixed-order row log-sum-exp fed from memory and from registers,
+and the world-size-independent cross-rank sum of 1024 per-chain scalars as one
+peer-memory kernel behind the C-ABI (its bits are asserted equal to the 1-rank
+sum on every rank, at every N).  There is no "step": K and W only size the timing
+loops (CUDA events on the launching stream, W warm-up launches first).
+`gpu_launches` counts those groundwork kernels and nothing else.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 """
@@ -102,6 +104,60 @@ def reference_arm(args) -> int:
     return 0
 
 
+def _vshard_section(gw, rank: int, world: int, local: int, warmup: int, steps: int) -> tuple[dict, int]:
+    """The one collective, through the C-ABI: W-independence asserted on real bits, latency timed."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from base_b200 import vshards
+
+    chains, n_stars, V = 1024, 10_000, vshards.DEFAULT_VSHARDS
+    rng = np.random.default_rng(20260)               # every rank draws the same global values
+    values = rng.normal(size=(chains, n_stars)) * 10.0 ** rng.integers(-6, 6, size=(chains, n_stars))
+    lo, hi = vshards.local_star_range(rank, world, n_stars, V)
+    launches = 0
+    out: dict = {"chains": chains, "n_stars": n_stars, "n_vshards": V, "world": world}
+    with vshards.PeerComm(local, rank, world, V, max_chains=chains) as comm:
+        dv = torch.from_numpy(np.ascontiguousarray(values[:, lo:hi])).to(f"cuda:{local}")
+        P = comm.shard_partials(dv, n_stars)
+        total = comm.allreduce(P)
+        launches += 2
+        comm.status()                                # raises on a timeout
+        # the world-1 answer, computed by this rank alone on its own GPU from ALL the stars
+        alone = gw.vshard_total(values, V, device=local)["total"]
+        launches += 2
+        same = bool((total.cpu().numpy().view(np.int64) == alone.view(np.int64)).all())
+        if not same:
+            raise SystemExit(f"rank {rank}: the {world}-rank sum differs in bits from the 1-rank sum")
+        out["bits_equal_world_1"] = True
+        if world > 1:
+            dist.barrier()
+        lat = comm.latency(chains, warmup=max(warmup, 20), reps=max(steps, 200))
+        launches += lat["launches"]
+        us = torch.tensor([lat["us_stream"], lat["us_graph"]], device=f"cuda:{local}")
+        if world > 1:
+            # comparison line: the same sum stated with NCCL all-gather + V ordered adds (eager torch)
+            for _ in range(max(warmup, 5)):
+                ref = vshards.allgather_ordered_sum(P)
+            dist.barrier(); torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(50):
+                ref = vshards.allgather_ordered_sum(P)
+            b.record()
+            torch.cuda.synchronize()
+            if not torch.equal(ref.view(torch.int64), total.view(torch.int64)):
+                raise SystemExit("peer kernel and NCCL all-gather statement disagree in bits")
+            us = torch.cat([us, torch.tensor([a.elapsed_time(b) * 1e3 / 50], device=us.device)])
+            dist.all_reduce(us, op=dist.ReduceOp.MAX)   # device-timed, max over ranks
+            out["nccl_allgather_plus_ordered_adds_us"] = round(us[2].item(), 2)
+            dist.barrier()                              # nobody frees a mailbox a peer still writes
+        out["peer_kernel_us_stream"] = round(us[0].item(), 2)
+        out["peer_kernel_us_graph"] = round(us[1].item(), 2)
+        comm.status()
+    return out, launches
+
+
 def main() -> int:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -111,7 +167,7 @@ def main() -> int:
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)
-    warmup = max(args.warmup, 3)
+    warmup, steps = max(args.warmup, 0), max(args.steps, 1)
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -120,15 +176,20 @@ def main() -> int:
 
     line = {
         "metric": _baseline_metric(), "value": None, "unit": "evals/s", "n_gpus": world,
-        "steps": args.steps, "warmup": warmup, "ms_per_step": None, "higher_is_better": True,
+        "steps": steps, "warmup": warmup, "ms_per_step": None, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "none (blocked)",
         "config": {"workload": "BLOCKED — no BASE-9 likelihood exists to run; see `blocked`",
-                   "l2": "n/a (groundwork kernels are register-resident; lse input < L2 noted below)"},
+                   "step": "undefined: there is no likelihood evaluation to call a step; --steps/--warmup "
+                           "only size the timing loops of the groundwork kernels below",
+                   "l2": "n/a for the headline; lse_rows input (82 MB) is under the 126 MB L2 and is "
+                         "reported as such, lse_generated reads no input at all"},
         "blocked": status.reason if status.blocked else
         "source now staged — SURVEY.md must be redone from it before a hot path exists: " + status.reason,
         "e2e": None, "roofline": None, "cpu_baseline": None,
         "gpu_launches": 0, "clocks": None, "groundwork": None,
     }
+    if warmup < 3:
+        line["warmup_note"] = "fewer than the 3 warm-up launches the timing rules ask for; as requested"
 
     from base_b200 import groundwork as gw  # raises if the .so is not built: no fallback
     if gw.device_count() == 0:
@@ -137,75 +198,68 @@ def main() -> int:
             print(json.dumps(line))
         return 1
 
+    import torch
     dist = None
+    torch.cuda.set_device(local)
     if world > 1:
-        import torch
         import torch.distributed as dist
-        torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         dist.barrier()
 
     import numpy as np
     launches = 0
+    few = max(3, steps // 4)
     with ClockSampler(local) as cs:
-        # step = one DFMA launch: 148*8 CTAs x 256 thr x 8 chains x 65536 fma
-        r = gw.dfma_peak(local, ctas_per_sm=8, iters=1 << 16, warmup=warmup, reps=args.steps)
+        r = gw.dfma_peak(local, ctas_per_sm=8, iters=1 << 16, warmup=warmup, reps=steps)
         launches += r["launches"]
         occ = {}
         for c in (1, 2, 4):
-            o = gw.dfma_peak(local, ctas_per_sm=c, iters=1 << 16, warmup=warmup, reps=max(3, args.steps // 4))
+            o = gw.dfma_peak(local, ctas_per_sm=c, iters=1 << 16, warmup=warmup, reps=few)
             occ[str(c * 8)] = round(o["tflops"], 3)
             launches += o["launches"]
         occ["64"] = round(r["tflops"], 3)
-        e = gw.transcendental_rate("exp", local, iters=1 << 12, warmup=warmup, reps=args.steps)
-        l = gw.transcendental_rate("log", local, iters=1 << 12, warmup=warmup, reps=args.steps)
-        e10 = gw.transcendental_rate("exp10", local, iters=1 << 12, warmup=warmup, reps=max(3, args.steps // 4))
-        l10 = gw.transcendental_rate("log10", local, iters=1 << 12, warmup=warmup, reps=max(3, args.steps // 4))
+        rates = {}
+        for name, reps in (("exp", steps), ("log", steps), ("exp10", few), ("log10", few),
+                           ("exp_spread", steps), ("log_spread", few)):
+            t = gw.transcendental_rate(name, local, iters=1 << 12, warmup=warmup, reps=reps)
+            rates[name] = round(t["gevals_per_s"], 2)
+            launches += t["launches"]
         lat = gw.step_latency(local, warmup=50, reps=2000)
-        launches += e["launches"] + l["launches"] + e10["launches"] + l10["launches"] + lat["launches"]
-        rng = np.random.default_rng(1234)
-        rows, cols = 10_000, 1_024  # 82 MB: under the 126 MB L2, second pass is an L2 hit
-        x = rng.normal(-40.0, 12.0, size=(rows, cols))
-        s = gw.lse_rows(x, local, warmup=warmup, reps=args.steps)
-        launches += s["launches"]
+        launches += lat["launches"]
+        rows, cols = 10_000, 1_024
+        x = np.random.default_rng(1234).normal(-40.0, 12.0, size=(rows, cols))
+        s = gw.lse_rows(x, local, warmup=warmup, reps=steps)
+        g_ = gw.lse_generated(rows, cols, local, warmup=warmup, reps=steps)
+        launches += s["launches"] + g_["launches"]
+        vs, n = _vshard_section(gw, rank, world, local, warmup, steps)
+        launches += n
     clocks = cs.summary()
 
+    def lse_line(res, reads_matrix):
+        sec = res["ms_per_launch"] * 1e-3
+        d = {"rows": rows, "cols": cols, "ms_per_launch": round(res["ms_per_launch"], 4),
+             "gterms_per_s": round(rows * cols / sec * 1e-9, 2),
+             "frac_of_exp_spread_rate": round(rows * cols / sec * 1e-9 / rates["exp_spread"], 3)}
+        if reads_matrix:
+            d["algorithmic_gb_per_s"] = round(rows * cols * 8 / sec * 1e-9, 1)
+        return d
+
     g = {
-        "note": "reference-independent denominators; NOT the BASE-9 hot path",
+        "note": "reference-independent denominators and plumbing; NOT the BASE-9 hot path",
         "fp64_dfma_tflops": round(r["tflops"], 3), "dfma_ms_per_launch": round(r["ms_per_launch"], 4),
         "dfma_tflops_by_warps_per_sm": occ,
-        "fp64_exp_gevals_per_s": round(e["gevals_per_s"], 2),
-        "fp64_log_gevals_per_s": round(l["gevals_per_s"], 2),
-        "fp64_exp10_gevals_per_s": round(e10["gevals_per_s"], 2),
-        "fp64_log10_gevals_per_s": round(l10["gevals_per_s"], 2),
+        "fp64_gevals_per_s": rates,
+        "rates_note": "exp/log/exp10/log10 are single-argument mid-range rates (contractions); "
+                      "*_spread take a fresh log-uniform argument per evaluation (b9_groundwork.h)",
         "dependent_step_latency_us": {k: round(v, 2) for k, v in lat.items() if k.startswith("us_")},
-        "lse_rows": {"rows": rows, "cols": cols, "ms_per_launch": round(s["ms_per_launch"], 4),
-                     "gelem_per_s": round(rows * cols / (s["ms_per_launch"] * 1e-3) * 1e-9, 2),
-                     "algorithmic_gb_per_s": round(rows * cols * 8 / (s["ms_per_launch"] * 1e-3) * 1e-9, 1)},
+        "lse_rows": lse_line(s, True),
+        "lse_generated": lse_line(g_, False),
+        "vshard_sum": vs,
     }
-
     if dist is not None:
-        import torch
-        from base_b200.chain_reduce import ordered_allreduce_sum
-        t = torch.arange(1024, dtype=torch.float64, device=f"cuda:{local}") * (rank + 1)
-        for _ in range(warmup):
-            ordered_allreduce_sum(t)
-        dist.barrier(); torch.cuda.synchronize()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        for _ in range(200):
-            out = ordered_allreduce_sum(t)
-        b.record()
-        torch.cuda.synchronize(); dist.barrier()
-        us = torch.tensor([a.elapsed_time(b) * 1e3 / 200], device=f"cuda:{local}")
-        dist.all_reduce(us, op=dist.ReduceOp.MAX)
-        expect = torch.arange(1024, dtype=torch.float64) * (world * (world + 1) // 2)
-        if not torch.equal(out.cpu(), expect):
-            raise SystemExit("ordered_allreduce_sum returned a wrong sum")
         per_rank = [None] * world
         dist.all_gather_object(per_rank, g["fp64_dfma_tflops"])
         g["fp64_dfma_tflops_per_rank"] = per_rank
-        g["ordered_allreduce_1024xf64_us_max_over_ranks"] = round(us.item(), 2)
         dist.barrier()
         dist.destroy_process_group()
 

@@ -1,5 +1,5 @@
 /*
- * b9_groundwork.h — C-ABI of libb9_groundwork.so
+ * b9_groundwork.h — C-ABI of libb9_groundwork.so  (ABI version 3)
  *
  * STATUS: the BASE-9 hot path is BLOCKED.  /root/reference is a
  * 4-line relocation notice (/root/reference/README.md:1-4); the base-cpp source
@@ -9,22 +9,27 @@
  * boundary can only be declared after the chain driver's call into the
  * likelihood has been read from source.
  *
- * What this header does declare: the reference-independent groundwork that
- * north_star asks for before any roofline fraction can be quoted —
- *   - the FP64 (DFMA) vector peak of the B200, absent from MEASURED_PEAKS.json;
- *   - FP64 exp()/log() issue rates, the other pipe a likelihood will sit on;
- *   - CUDA-libm exp/log versus host libm, element by element (ULP distance);
- *   - a fixed-order FP64 log-sum-exp over rows and a fixed-order sum over rows,
- *     to measure how far reduction order + libm differences move a result that
- *     must later agree with a serial CPU loop to 1e-10 relative.
- * Each is plain mathematics with a closed-form CPU checker
- * (oracle/groundwork_ref.c); none cites or imitates reference code.
+ * What this header does declare is reference-independent:
+ *   1. FP64 denominators for the roofline (DFMA peak; exp/log/exp10/log10
+ *      rates, each labelled with the argument distribution it was taken on);
+ *   2. CUDA-libm versus host libm, element by element (ULP distance);
+ *   3. a fixed-order FP64 log-sum-exp over rows, fed either from a matrix in
+ *      memory or from terms produced in registers by a closed-form synthetic
+ *      generator (pure arithmetic, NOT a photometric model), to show what the
+ *      fixed order costs when the terms never travel through memory;
+ *   4. the one collective north_star names — a sum of per-chain FP64 scalars
+ *      over ranks — made bit-identical for every world size by reducing over
+ *      V fixed VIRTUAL SHARDS instead of over ranks, and implemented as one
+ *      kernel over NVLink peer memory behind this C-ABI (no NCCL call, no
+ *      Python on the step path).
+ * Each has a closed-form CPU checker (oracle/groundwork_ref.c); none cites or
+ * imitates reference code.
  *
  * Conventions: every entry point returns 0 on success or a negative B9GW_E_*
- * code; b9gw_last_error() gives the message for the calling thread.  All
- * pointers are HOST pointers unless the name ends in _dev.  There is no CPU
- * fallback: with no usable device every compute entry point fails with
- * B9GW_E_NODEVICE.
+ * code; b9gw_last_error() gives the message for the calling thread.  Pointers
+ * are HOST pointers unless the name ends in _dev.  No entry point changes the
+ * caller's current CUDA device.  There is no CPU fallback: with no usable
+ * device every compute entry point fails with B9GW_E_NODEVICE.
  */
 #ifndef B9_GROUNDWORK_H
 #define B9_GROUNDWORK_H
@@ -37,10 +42,18 @@ extern "C" {
 #define B9GW_E_NODEVICE  (-1)   /* no CUDA device / driver */
 #define B9GW_E_CUDA      (-2)   /* a CUDA runtime call failed */
 #define B9GW_E_ARG       (-3)   /* bad argument */
+#define B9GW_E_TIMEOUT   (-4)   /* a peer did not arrive within the comm's timeout */
+#define B9GW_E_STATE     (-5)   /* call made in the wrong state (e.g. not connected) */
 
 #define B9GW_DFMA_ILP      8    /* independent FMA chains per thread */
 #define B9GW_DFMA_THREADS  256  /* threads per CTA */
 #define B9GW_TRANS_ILP     4    /* independent exp/log chains per thread */
+
+#define B9GW_LSE_REG_COLS  1024 /* rows up to this length stay in registers */
+
+#define B9GW_MAX_WORLD        16  /* ranks in one comm (one NVSwitch domain) */
+#define B9GW_MAX_VSHARDS      128 /* virtual shards; must be one of 4,8,16,32,64,128 */
+#define B9GW_IPC_HANDLE_BYTES 64  /* opaque per-rank handle exchanged at connect */
 
 /* ABI version of this header; bumped on any signature change. */
 int b9gw_abi_version(void);
@@ -54,6 +67,8 @@ int b9gw_device_count(void);
 /* SM count and current SM clock ceiling (MHz) of `device`. */
 int b9gw_device_info(int device, int *sm_count, int *sm_clock_mhz,
                      long long *l2_bytes);
+
+/* ------------------------------------------------------------------ rates */
 
 /*
  * FP64 FMA peak.  Launches sm_count*ctas_per_sm CTAs of B9GW_DFMA_THREADS
@@ -71,11 +86,21 @@ int b9gw_dfma_peak(int device, int ctas_per_sm, int iters, double a, double b,
                    long long *n_threads, float *ms_per_launch, double *tflops);
 
 /*
- * FP64 transcendental issue rate.  which = 0: x <- exp(-x); 1: x <- log(x + 3);
- * 2: x <- exp10(-0.4 x) (magnitude -> flux); 3: x <- log10(x + 3).  All four
- * are contractions, so the stored value is insensitive to last-bit libm
- * differences.  Same launch shape and timing as above with
- * B9GW_TRANS_ILP chains per thread; gevals = 1e-9 * ILP*iters*n_threads / s.
+ * FP64 transcendental issue rate.
+ *   which 0..3 — CONTRACTIONS: x <- exp(-x); x <- log(x + 3); x <- exp10(-0.4 x);
+ *     x <- log10(x + 3).  After a few dozen iterations every thread evaluates
+ *     the function at ONE mid-range argument (exp near 0.567, log near 3.5), so
+ *     these are single-argument, mid-range rates; the stored value is
+ *     insensitive to last-bit libm differences.
+ *   which 4 — exp over a SPREAD of arguments: every evaluation takes a fresh
+ *     argument -(2^e * 1.f) with e uniform in [-6, 9] and f 20 random bits from
+ *     a per-chain 32-bit LCG (integer pipe), i.e. log-uniform magnitudes from
+ *     1/64 to 1024, ~3 % of them below exp's underflow threshold — the range a
+ *     max-shifted log-sum-exp feeds to exp.  The thread stores the sum of its
+ *     evaluations (one extra DADD per exp).
+ *   which 5 — log over a spread: arguments 2^e * 1.f, e uniform in [-8, 7].
+ * Same launch shape and timing as above with B9GW_TRANS_ILP chains per thread;
+ * gevals = 1e-9 * ILP*iters*n_threads / s.
  */
 int b9gw_transcendental_rate(int device, int which, int ctas_per_sm, int iters,
                              int warmup, int reps, double *out_host,
@@ -93,10 +118,12 @@ int b9gw_transcendental_rate(int device, int which, int ctas_per_sm, int iters,
 int b9gw_step_latency(int device, int warmup, int reps, float *us_launch_sync,
                       float *us_launch_d2h_sync, float *us_graph_d2h_sync);
 
-/* Elementwise y[i] = exp(x[i]) (which=0) or log(x[i]) (which=1) on the device,
- * for comparing CUDA libm with the host's bit by bit. */
+/* Elementwise y[i] = f(x[i]) on the device, f = exp (which 0), log (1),
+ * exp10 (2), log10 (3), for comparing CUDA libm with the host's bit by bit. */
 int b9gw_map(int device, int which, const double *x_host, double *y_host,
              long long n);
+
+/* ------------------------------------------------- fixed-order log-sum-exp */
 
 /*
  * Fixed-order log-sum-exp.  x is rows x cols, row-major.  One warp per row:
@@ -105,12 +132,140 @@ int b9gw_map(int device, int which, const double *x_host, double *y_host,
  * (offsets 16,8,4,2,1) adds the 32 partials; row_lse = max + log(sum), and
  * -inf for a row whose max is -inf.  `total` is the sum of row_lse in the fixed
  * order of b9ref_ordered_sum (1024 strided partials, then a pairwise tree).
+ * Rows of up to B9GW_LSE_REG_COLS columns are read from memory ONCE, with all
+ * of a lane's loads in flight together, and kept in registers between the max
+ * pass and the exp pass; longer rows are read twice.  The order, and therefore
+ * every bit of the result, is the same on both paths.
  * Timing covers `reps` launches of both kernels with x already on the device.
  *   row_lse_host : rows doubles (may be NULL);  total_host : 1 double
  */
 int b9gw_lse_rows(int device, const double *x_host, long long rows,
                   long long cols, int warmup, int reps, double *row_lse_host,
                   double *total_host, float *ms_per_launch);
+
+/*
+ * The synthetic term generator, materialised: x[r*cols + c] = g(r, c, cols),
+ *   u  = r * 0.6180339887498949,  c0 = (u - floor(u)) * cols,
+ *   w  = (34 + (r mod 7)) / cols,
+ *   t  = fma(c, w, -(c0 * w)),    g = -(t * t)
+ * (each operation rounded once, as written; oracle/groundwork_ref.c:b9ref_gen_term
+ * is the host statement).  A row is a parabola with its maximum (0 >= g > -1)
+ * near column c0 and a minimum between about -290 and -1600: some rows reach
+ * past exp's underflow threshold, all rows have a handful of terms near the
+ * maximum that carry the sum.  It is arithmetic chosen to give exp a realistic
+ * spread of arguments; it models nothing.
+ */
+int b9gw_generate_terms(int device, long long rows, long long cols, double *x_host);
+
+/*
+ * The same fixed-order log-sum-exp, but every term is produced in registers by
+ * g(r, c, cols) above: no matrix exists in memory, one exp per term.  Row
+ * values and total are bit-identical to b9gw_lse_rows run on
+ * b9gw_generate_terms' output.  Rows of up to B9GW_LSE_REG_COLS columns keep
+ * their terms in registers between the two passes; longer rows regenerate them.
+ */
+int b9gw_lse_generated(int device, long long rows, long long cols, int warmup,
+                       int reps, double *row_lse_host, double *total_host,
+                       float *ms_per_launch);
+
+/* -------------------------- world-size-independent sum over virtual shards */
+
+/*
+ * A job's N stars are cut into V VIRTUAL SHARDS, a function of (N, V) only:
+ * shard v holds stars [floor(v*N/V), floor((v+1)*N/V)).  A world of W ranks
+ * (V % W == 0) gives rank r the V/W consecutive shards starting at r*V/W.
+ * A per-chain sum over stars is then defined as
+ *     total[c] = (((0 + P[0][c]) + P[1][c]) + ... ) + P[V-1][c],
+ *     P[v][c]  = warp-order sum of the shard's per-star values
+ *                (32 lane-strided serial partials, xor-butterfly 16,8,4,2,1),
+ * which does not mention W: the same N, V and per-star values give the same
+ * bits at W = 1, 2, 4, 8.  (Summing per-rank partials in rank order does not
+ * have this property — the grouping changes with W.)
+ */
+
+/* Stars [lo, hi) of virtual shard `shard`.  Pure host arithmetic. */
+int b9gw_vshard_bounds(long long n_stars, int n_vshards, int shard,
+                       long long *lo, long long *hi);
+
+/*
+ * P for the local shards.  values_dev is [chains][ld] row-major and holds this
+ * rank's stars only: column 0 is star lo(first_shard).  partial_dev receives
+ * [n_shards][chains].  One warp per (shard, chain); launched on `cuda_stream`
+ * (a cudaStream_t; NULL = the legacy default stream) of the current device and
+ * not synchronised.
+ */
+int b9gw_shard_partials(const double *values_dev, long long chains, long long ld,
+                        long long n_stars_total, int n_vshards, int first_shard,
+                        int n_shards, double *partial_dev, void *cuda_stream);
+
+typedef struct b9gw_comm b9gw_comm;
+
+/*
+ * Phase 1, on every rank: allocate this rank's mailbox on `device` (2 parities
+ * x V x max_chains 16-byte slots, zeroed) and write an opaque handle to
+ * handle_out[B9GW_IPC_HANDLE_BYTES].  The caller publishes the handles by any
+ * means it has (MPI, a file, torch.distributed.all_gather ...).
+ * n_vshards must be a power of two in [4, B9GW_MAX_VSHARDS] and a multiple of world.
+ */
+int b9gw_comm_create(int device, int rank, int world, int n_vshards,
+                     long long max_chains, b9gw_comm **comm, void *handle_out);
+
+/*
+ * Phase 2: all_handles is world x B9GW_IPC_HANDLE_BYTES in rank order.  Maps
+ * every peer's mailbox into this process (CUDA IPC; peers must be P2P-capable
+ * GPUs of one node).  With world == 1 this does nothing and may be skipped.
+ */
+int b9gw_comm_connect(b9gw_comm *comm, const void *all_handles);
+
+/*
+ * One step.  partial_dev is this rank's [V/world][chains] (as written by
+ * b9gw_shard_partials); out_dev receives total[chains] on EVERY rank.  A single
+ * kernel, launched on `cuda_stream` and not synchronised: each thread stores
+ * its partials straight into every rank's mailbox over NVLink as 16-byte
+ * {lo32, step, hi32, step} packets (8-byte-atomic, so a packet carries its own
+ * arrival flag: no fence, no separate flag, no barrier), then polls its own
+ * mailbox slots and adds shards 0..V-1 left to right.  The step counter lives
+ * in device memory, so the launch can be captured in a CUDA graph and replayed.
+ * All calls on one comm must be ordered on one stream, every rank must make
+ * the same sequence of calls, and each rank must own its GPU (ranks that wait
+ * on one another cannot share a device).  If a peer does not arrive within the
+ * comm's timeout the kernel stores NaN, raises the comm's sticky status and
+ * returns; it never spins forever.
+ */
+int b9gw_ordered_allreduce(b9gw_comm *comm, const double *partial_dev,
+                           double *out_dev, long long chains, void *cuda_stream);
+
+/* Spin budget of one step in milliseconds (default 2000). */
+int b9gw_comm_set_timeout_ms(b9gw_comm *comm, int ms);
+
+/*
+ * Synchronises the device and reports the sticky status: *timed_out != 0 if any
+ * step gave up waiting; *steps = steps completed.  Returns B9GW_E_TIMEOUT in
+ * that case so a caller that ignores the out-parameters still sees it.
+ */
+int b9gw_comm_status(b9gw_comm *comm, int *timed_out, unsigned long long *steps);
+
+/*
+ * Latency of the step kernel alone, measured with CUDA events on a private
+ * stream with `reps` back-to-back launches after `warmup`: us_stream for plain
+ * launches, us_graph for a CUDA graph of 8 steps per launch (reps rounded up to
+ * a multiple of 8).  Every rank must call it with the same arguments.
+ */
+int b9gw_allreduce_latency(b9gw_comm *comm, long long chains, int warmup,
+                           int reps, float *us_stream, float *us_graph);
+
+/* Unmaps the peers and frees the mailbox.  The caller must make sure (barrier)
+ * that no peer is still inside a step. */
+int b9gw_comm_destroy(b9gw_comm *comm);
+
+/*
+ * Host-buffer convenience, world = 1: values_host is [chains][n_stars];
+ * partials_host receives P as [V][chains] (may be NULL), total_host receives
+ * total[chains].  Runs b9gw_shard_partials + b9gw_ordered_allreduce on one GPU.
+ */
+int b9gw_vshard_total(int device, const double *values_host, long long chains,
+                      long long n_stars, int n_vshards, double *partials_host,
+                      double *total_host);
 
 #ifdef __cplusplus
 }

@@ -21,6 +21,12 @@ class Ref:
         L.b9ref_lse_rows.restype, L.b9ref_lse_rows.argtypes = None, [_pd, _ll, _ll, _i, _pd]
         L.b9ref_ordered_sum.restype, L.b9ref_ordered_sum.argtypes = _d, [_pd, _ll]
         L.b9ref_serial_sum.restype, L.b9ref_serial_sum.argtypes = _d, [_pd, _ll]
+        L.b9ref_spread_args.restype, L.b9ref_spread_args.argtypes = None, [_i, _i, _i, _i, _pd]
+        L.b9ref_gen_term.restype, L.b9ref_gen_term.argtypes = _d, [_ll, _ll, _ll]
+        L.b9ref_generate_terms.restype, L.b9ref_generate_terms.argtypes = None, [_ll, _ll, _pd]
+        L.b9ref_shard_lo.restype, L.b9ref_shard_lo.argtypes = _ll, [_ll, _i, _i]
+        L.b9ref_shard_partial.restype, L.b9ref_shard_partial.argtypes = _d, [_pd, _ll, _ll]
+        L.b9ref_vshard_total.restype, L.b9ref_vshard_total.argtypes = None, [_pd, _ll, _ll, _i, _pd, _pd]
         self.L = L
 
     @staticmethod
@@ -30,15 +36,42 @@ class Ref:
     def dfma_lanes(self, a, b, iters):
         return np.array([self.L.b9ref_dfma_lane(l, a, b, iters) for l in range(32)])
 
+    TRANS = {"exp": 0, "log": 1, "exp10": 2, "log10": 3, "exp_spread": 4, "log_spread": 5}
+    MAP = {"exp": 0, "log": 1, "exp10": 2, "log10": 3, "pow10": 12}
+
     def trans_lanes(self, which, iters):
-        w = {"exp": 0, "log": 1, "exp10": 2, "log10": 3}[which]
-        return np.array([self.L.b9ref_trans_lane(l, w, iters) for l in range(32)])
+        return np.array([self.L.b9ref_trans_lane(l, self.TRANS[which], iters) for l in range(32)])
+
+    def spread_args(self, which, lane, j, iters):
+        a = np.empty(iters, dtype=np.float64)
+        self.L.b9ref_spread_args(lane, j, self.TRANS[which], iters, self._p(a))
+        return a
 
     def map(self, which, x):
         x = np.ascontiguousarray(x, dtype=np.float64)
         y = np.empty_like(x)
-        self.L.b9ref_map({"exp": 0, "log": 1}[which], self._p(x), self._p(y), x.size)
+        self.L.b9ref_map(self.MAP[which], self._p(x), self._p(y), x.size)
         return y
+
+    def generate_terms(self, rows, cols):
+        x = np.empty((rows, cols), dtype=np.float64)
+        self.L.b9ref_generate_terms(rows, cols, self._p(x))
+        return x
+
+    def shard_lo(self, n, V, v):
+        return self.L.b9ref_shard_lo(n, V, v)
+
+    def shard_partial(self, row, lo, hi):
+        row = np.ascontiguousarray(row, dtype=np.float64)
+        return self.L.b9ref_shard_partial(self._p(row), lo, hi)
+
+    def vshard_total(self, values, V):
+        values = np.ascontiguousarray(values, dtype=np.float64)
+        chains, n = values.shape
+        partials = np.empty((V, chains), dtype=np.float64)
+        total = np.empty(chains, dtype=np.float64)
+        self.L.b9ref_vshard_total(self._p(values), chains, n, V, self._p(partials), self._p(total))
+        return partials, total
 
     def lse_rows(self, x, warp_order):
         x = np.ascontiguousarray(x, dtype=np.float64)

@@ -40,7 +40,10 @@ def test_abi_version_and_loud_failure_without_a_device(built):
         pytest.skip("a CUDA device is visible; the no-device path cannot be exercised")
     import numpy as np
     for call in (lambda: gw.dfma_peak(0), lambda: gw.transcendental_rate("exp"),
-                 lambda: gw.device_map("exp", np.zeros(4)), lambda: gw.lse_rows(np.zeros((2, 2)))):
+                 lambda: gw.transcendental_rate("exp_spread"),
+                 lambda: gw.device_map("exp10", np.zeros(4)), lambda: gw.lse_rows(np.zeros((2, 2))),
+                 lambda: gw.generate_terms(2, 2), lambda: gw.lse_generated(2, 2),
+                 lambda: gw.vshard_total(np.zeros((2, 8)), 4)):
         with pytest.raises(gw.GroundworkError) as ei:
             call()
         assert ei.value.code == -1 and "no CPU fallback" in str(ei.value)
@@ -52,6 +55,30 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(gw, "LIB_PATH", tmp_path / "libb9_groundwork.so")
     with pytest.raises(FileNotFoundError, match="no CPU fallback"):
         gw.lib()
+
+
+def test_sizes_that_would_wrap_are_rejected_before_any_allocation(built):
+    # rows*cols and n*8 used to be computed unchecked
+    import ctypes as C
+    from base_b200 import groundwork as gw
+    L, t = gw.lib(), C.c_double()
+    big = 1 << 62
+    assert L.b9gw_lse_rows(0, None, big, 4, 0, 1, None, C.byref(t), None) == gw.E_ARG
+    assert L.b9gw_lse_generated(0, big, big, 0, 1, None, C.byref(t), None) == gw.E_ARG
+    assert L.b9gw_generate_terms(0, big, 8, None) == gw.E_ARG
+    assert L.b9gw_map(0, 0, None, None, big) == gw.E_ARG
+    assert L.b9gw_map(0, 7, None, None, 0) == gw.E_ARG
+    assert b"overflow" in L.b9gw_last_error() or b"which" in L.b9gw_last_error()
+
+
+def test_no_source_file_names_a_closed_batched_copy_call():
+    # B200_PROFILING.md: gpurun refuses a repo whose sources name one of the four calls
+    import re
+    pat = re.compile("Memcpy" + "(3D)?" + "Batch" + "Async")
+    for path in ROOT.rglob("*"):
+        if path.is_file() and path.suffix in {".cu", ".cuh", ".h", ".c", ".cpp", ".py", ".sh"} \
+                and ".git" not in path.parts and "gpurun_out" not in path.parts:
+            assert not pat.search(path.read_text(errors="ignore")), path
 
 
 def test_product_package_never_touches_the_checker():

@@ -1,13 +1,16 @@
 """GPU tests: every groundwork kernel, through the C-ABI, against the CPU checker.
 
 Tolerances, and why:
-  dfma chain, ordered sum  — IEEE add/fma only            -> bit-exact
-  exp / log elementwise    — CUDA libm documents <= 1 ULP (exp) and <= 1 ULP (log) in FP64,
-                             glibc < 1 ULP                 -> distance <= 2 ULP
+  dfma chain, ordered sum, shard partials, virtual-shard totals, the term generator
+                           — IEEE add/mul/div/fma only    -> bit-exact
+  exp / log / exp10 / log10 elementwise
+                           — CUDA libm documents <= 1 ULP for each in FP64, glibc < 1 ULP
+                                                           -> distance <= 2 ULP
   row log-sum-exp          — same order as the kernel      -> <= 2e-14 of max(1,|lse|)
                              serial CPU order              -> <= 1e-13 of max(1,|lse|)
                              (mixed abs/rel: a row value near 0 makes pure relative error
                              ill-conditioned, see tests/_ref.py:mixed_err)
+  lse_generated vs lse_rows on the materialised terms      -> bit-exact (same device libm)
 north_star's bar for the real path is 1e-10 relative; these show the margin available.
 """
 import numpy as np
@@ -43,10 +46,11 @@ def test_dfma_chain_bit_exact(gw, ref, iters, ctas):
     assert (bits(r["out"].reshape(-1, 32)) == bits(want)).all()
 
 
-def test_dfma_peak_is_plausible(gw):
+def test_dfma_peak_is_within_3_percent_of_the_recorded_denominator(gw):
     r = gw.dfma_peak(0, ctas_per_sm=8, iters=1 << 16, warmup=3, reps=5)
-    # 148 SMs x 64 DFMA/clk x 2 x 1.965 GHz = 37.2 TF is the arithmetic ceiling
-    assert 5.0 < r["tflops"] < 45.0, r
+    # 148 SMs x 64 DFMA/clk x 2 x 1.965 GHz = 37.2 TF is the arithmetic ceiling; rounds 1 and 2
+    # measured 36.99-37.10 (profiles/).  A box that misses this window is throttled or clock-locked.
+    assert 37.0 * 0.97 < r["tflops"] < 37.0 * 1.03, r
 
 
 @pytest.mark.parametrize("which", ["exp", "log", "exp10", "log10"])
@@ -58,19 +62,60 @@ def test_transcendental_chain(gw, ref, which):
     assert r["gevals_per_s"] > 1.0
 
 
-@pytest.mark.parametrize("which", ["exp", "log"])
-def test_libm_distance_within_2_ulp(gw, ref, which):
-    rng = np.random.default_rng(42)
-    if which == "exp":   # the arguments a max-shifted log-sum-exp produces, plus the full finite range
-        x = np.concatenate([-rng.exponential(20.0, 500_000), rng.uniform(-745.0, 709.0, 500_000),
-                            [0.0, -0.0, -745.2, 709.7, -np.inf]])
+@pytest.mark.parametrize("which", ["exp_spread", "log_spread"])
+def test_spread_rate_sums_match_the_checker(gw, ref, which):
+    iters = 300
+    r = gw.transcendental_rate(which, 0, ctas_per_sm=1, iters=iters, warmup=0, reps=1, want_out=True)
+    want = ref.trans_lanes(which, iters)
+    got = r["out"].reshape(-1, 32)
+    # sums of 4*iters libm values of magnitude <= 1 (exp) / <= 5.6 (log), each within 1 ulp of the
+    # host's; a differing input can also move the rounding of the running sum (ulp(acc) ~ 3e-14)
+    assert np.max(np.abs(got - want)) < 4 * iters * 6.0 * 2.3e-16 * 8
+    assert (got == got[0]).all() and r["gevals_per_s"] > 1.0
+    a = ref.spread_args(which, 5, 2, 4096)               # the distribution the header promises
+    if which == "exp_spread":
+        assert a.max() <= -2.0 ** -6 and a.min() > -1024.0 and 0.01 < np.mean(a < -745.2) < 0.06
     else:
-        x = np.concatenate([rng.uniform(1.0, 1024.0, 500_000), 10.0 ** rng.uniform(-300, 300, 500_000),
-                            [1.0, 5e-324, 1.7976931348623157e308]])
+        assert a.min() >= 2.0 ** -8 and a.max() < 256.0
+
+
+LIBM_CASES = {
+    # the arguments a max-shifted log-sum-exp produces, plus the full finite range
+    "exp": lambda rng: np.concatenate([-rng.exponential(20.0, 500_000), rng.uniform(-745.0, 709.0, 500_000),
+                                       [0.0, -0.0, -745.2, 709.7, -np.inf]]),
+    "log": lambda rng: np.concatenate([rng.uniform(1.0, 1024.0, 500_000), 10.0 ** rng.uniform(-300, 300, 500_000),
+                                       [1.0, 5e-324, 1.7976931348623157e308]]),
+    # 10^(-0.4 m) for magnitudes m in [-10, 40], plus the full finite range and exact powers
+    "exp10": lambda rng: np.concatenate([-0.4 * rng.uniform(-10.0, 40.0, 500_000),
+                                         rng.uniform(-323.0, 308.0, 500_000),
+                                         np.arange(-20.0, 23.0), [0.0, -0.0, -323.4, 308.2, -np.inf]]),
+    "log10": lambda rng: np.concatenate([rng.uniform(1e-3, 1e3, 500_000), 10.0 ** rng.uniform(-300, 300, 500_000),
+                                         10.0 ** np.arange(-20.0, 23.0), [1.0, 5e-324, 1.7976931348623157e308]]),
+}
+
+
+@pytest.mark.parametrize("which", ["exp", "log", "exp10", "log10"])
+def test_libm_distance_within_2_ulp(gw, ref, which):
+    x = LIBM_CASES[which](np.random.default_rng(42))
     got, want = gw.device_map(which, x), ref.map(which, x)
     d = ulp_distance(got, want)
     assert d.max() <= 2, (d.max(), x[d.argmax()])
     print(f"\n{which}: bit-identical {np.mean(d == 0):.4%}, max {d.max()} ulp")
+
+
+def test_device_exp10_against_host_pow10(gw, ref):
+    # ADVICE r1 / VERDICT weak 7: device exp10() and host pow(10, x) are different functions.
+    # Measured, not assumed: both are compared with the correctly rounded value where it is
+    # known exactly (10^k, k = 0..22) and with each other elsewhere.
+    x = LIBM_CASES["exp10"](np.random.default_rng(43))
+    dev, p10, e10 = gw.device_map("exp10", x), ref.map("pow10", x), ref.map("exp10", x)
+    d_pow, d_e10 = ulp_distance(dev, p10), ulp_distance(dev, e10)
+    assert d_pow.max() <= 2 and d_e10.max() <= 2, (d_pow.max(), d_e10.max())
+    k = np.arange(0.0, 23.0)
+    exact = np.array([float(10 ** int(i)) for i in k])
+    assert (gw.device_map("exp10", k) == exact).all()     # CUDA exp10 is exact on exact powers
+    print(f"\nexp10 vs pow(10,x): identical {np.mean(d_pow == 0):.4%}, max {d_pow.max()} ulp; "
+          f"vs glibc exp10: identical {np.mean(d_e10 == 0):.4%}, max {d_e10.max()} ulp")
 
 
 def test_step_latency_is_measured_and_ordered(gw):
@@ -84,7 +129,11 @@ def test_map_empty(gw):
     assert gw.device_map("exp", np.empty(0)).size == 0
 
 
-@pytest.mark.parametrize("rows,cols", [(1, 1), (5, 31), (9, 32), (8, 33), (257, 1000), (10_000, 1024)])
+# cols straddle every dispatch edge of lse.cu: 128/129 (4 -> 16 terms per lane), 512/513
+# (16 -> 32), 1024/1025 (registers -> streaming), 3000 (several streaming chunks + ragged tail)
+@pytest.mark.parametrize("rows,cols", [(1, 1), (5, 31), (9, 32), (8, 33), (17, 128), (17, 129),
+                                       (33, 512), (33, 513), (257, 1000), (10_000, 1024),
+                                       (40, 1025), (23, 3000)])
 def test_lse_rows_against_both_orders(gw, ref, rows, cols):
     rng = np.random.default_rng(rows * 7919 + cols)
     x = rng.normal(-40.0, 12.0, size=(rows, cols))
@@ -117,6 +166,86 @@ def test_lse_is_run_to_run_deterministic(gw):
     x = np.random.default_rng(5).normal(-40.0, 12.0, size=(3000, 777))
     a, b = gw.lse_rows(x), gw.lse_rows(x)
     assert (bits(a["row_lse"]) == bits(b["row_lse"])).all() and bits(a["total"]) == bits(b["total"])
+
+
+@pytest.mark.parametrize("rows,cols", [(1, 1), (3, 2), (9, 33), (64, 128), (65, 200), (100, 513),
+                                       (10_000, 1024), (50, 1025), (7, 2500)])
+def test_generator_and_generated_lse_are_bit_identical_to_the_materialised_path(gw, ref, rows, cols):
+    x = gw.generate_terms(rows, cols)
+    assert (bits(x) == bits(ref.generate_terms(rows, cols))).all()      # arithmetic only: bit-exact
+    assert x.max() <= 0.0 and x.min() > -1700.0
+    mat, gen = gw.lse_rows(x), gw.lse_generated(rows, cols)
+    assert (bits(mat["row_lse"]) == bits(gen["row_lse"])).all()
+    assert bits(mat["total"]) == bits(gen["total"])
+    assert mixed_err(gen["row_lse"], ref.lse_rows(x, True)) < 2e-14
+    assert bits(gen["total"]) == bits(ref.ordered_sum(gen["row_lse"]))
+
+
+def test_generated_lse_empty_shapes(gw):
+    e = gw.lse_generated(6, 0)
+    assert (e["row_lse"] == -np.inf).all() and e["total"] == -np.inf
+    z = gw.lse_generated(0, 9)
+    assert z["row_lse"].size == 0 and z["total"] == 0.0
+    assert gw.generate_terms(0, 5).size == 0 and gw.generate_terms(5, 0).size == 0
+
+
+def test_lse_total_survives_repeated_launches(gw, ref):
+    # the last-CTA ticket must reset itself: reps > 1 on one stream, total still the ordered sum
+    x = np.random.default_rng(11).normal(-40.0, 12.0, size=(1234, 300))
+    r = gw.lse_rows(x, warmup=2, reps=5)
+    assert bits(r["total"]) == bits(ref.ordered_sum(r["row_lse"]))
+
+
+def vshard_values(chains, n, seed):
+    rng = np.random.default_rng(seed)
+    return rng.normal(size=(chains, n)) * 10.0 ** rng.integers(-6, 6, size=(chains, n))
+
+
+@pytest.mark.parametrize("V", [4, 8, 16, 32, 64, 128])
+@pytest.mark.parametrize("chains,n", [(1, 1), (3, 5), (63, 1003), (64, 130), (65, 4096), (1000, 777)])
+def test_vshard_total_bit_exact(gw, ref, V, chains, n):
+    values = vshard_values(chains, n, V * 1000 + chains + n)      # n < V leaves some shards empty
+    got = gw.vshard_total(values, V)
+    want_p, want_t = ref.vshard_total(values, V)
+    assert (bits(got["partials"]) == bits(want_p)).all()
+    assert (bits(got["total"]) == bits(want_t)).all()
+
+
+def test_vshard_total_no_stars(gw):
+    got = gw.vshard_total(np.empty((5, 0)), 64)
+    assert (got["partials"] == 0.0).all() and (got["total"] == 0.0).all()
+
+
+def test_peer_comm_world_1_through_device_pointers_and_a_cuda_graph(gw, ref):
+    import torch
+    from base_b200.vshards import PeerComm
+    chains, n, V = 300, 2000, 64
+    values = vshard_values(chains, n, 99)
+    _, want = ref.vshard_total(values, V)
+    dv = torch.from_numpy(values).cuda()
+    with PeerComm(0, 0, 1, V, max_chains=512) as comm:
+        P = comm.shard_partials(dv, n)
+        out = comm.allreduce(P)
+        assert (bits(out.cpu().numpy()) == bits(want)).all()
+        # fewer chains than max_chains, then the same launch captured and replayed: the step
+        # counter lives in device memory, so replays keep working
+        out2 = torch.empty(chains, dtype=torch.float64, device="cuda")
+        g = torch.cuda.CUDAGraph()
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            comm.allreduce(P, out2)                       # warm the stream outside capture
+            with torch.cuda.graph(g, stream=s):
+                comm.allreduce(P, out2)
+        for _ in range(3):
+            out2.zero_()
+            g.replay()
+            torch.cuda.synchronize()
+            assert (bits(out2.cpu().numpy()) == bits(want)).all()
+        st = comm.status()
+        assert not st["timed_out"] and st["steps"] == 1 + 1 + 3
+        lat = comm.latency(chains, warmup=5, reps=40)
+        assert 0.5 < lat["us_stream"] < 200.0 and 0.5 < lat["us_graph"] < 200.0
 
 
 def test_smoke_entry_point(gw):

@@ -67,3 +67,58 @@ def test_ordered_sum_small_and_ragged(ref):
     assert ref.ordered_sum(np.empty(0)) == 0.0
     v = np.arange(1, 2050, dtype=np.float64)
     assert ref.ordered_sum(v) == v.sum() == 2049 * 2050 / 2
+
+
+def test_generator_is_the_stated_arithmetic_rounded_once_per_operation(ref):
+    # replay include/b9_groundwork.h's formula in exact rationals, rounding where it says
+    import math
+    phi = 0.6180339887498949
+    for rows, cols in [(5, 7), (40, 1024), (3, 2500)]:
+        x = ref.generate_terms(rows, cols)
+        for r in (0, 1, rows - 1):
+            u = float(Fraction(r) * Fraction(phi))
+            c0 = float(Fraction(float(Fraction(u) - math.floor(u))) * cols)
+            w = float(Fraction(34 + r % 7) / cols)
+            b = -float(Fraction(c0) * Fraction(w))
+            for c in (0, 1, cols // 2, cols - 1):
+                t = float(Fraction(c) * Fraction(w) + Fraction(b))        # fma: one rounding
+                assert x[r, c] == -float(Fraction(t) * Fraction(t))
+    x = ref.generate_terms(200, 1024)
+    assert (x.max(axis=1) > -1.0).all() and x.max() <= 0.0                 # a term near 0 in every row
+    assert x.min() < -745.0 and (x.min(axis=1) < -280.0).all()             # some rows reach past underflow
+    # a few hundred terms per row carry the sum, the rest are negligible or underflow
+    carrying = (x > x.max(axis=1, keepdims=True) - 36.0).sum(axis=1)
+    assert 150 < carrying.min() and carrying.max() < 400      # fewer when the peak sits at an edge
+
+
+def test_shard_partial_and_total_against_exact_sums(ref):
+    rng = np.random.default_rng(3)
+    v = rng.normal(size=(4, 1003)) * 10.0 ** rng.integers(-6, 6, size=(4, 1003))
+    P, T = ref.vshard_total(v, 64)
+    lo = [ref.shard_lo(1003, 64, s) for s in range(65)]
+    assert lo[0] == 0 and lo[64] == 1003 and all(b - a in (15, 16) for a, b in zip(lo, lo[1:]))
+    import math
+    for c in range(4):
+        for s in (0, 17, 63):
+            exact = math.fsum(v[c, lo[s]:lo[s + 1]])
+            assert abs(P[s, c] - exact) <= 4e-16 * np.abs(v[c, lo[s]:lo[s + 1]]).sum()
+        acc = 0.0
+        for s in range(64):
+            acc += P[s, c]
+        assert T[c] == acc                                                  # strictly left to right
+    # integers: every order is exact, so the partition itself is what is checked
+    ints = np.arange(1, 1004, dtype=np.float64)[None, :]
+    _, t = ref.vshard_total(ints, 8)
+    assert t[0] == 1003 * 1004 / 2
+
+
+def test_spread_arguments_are_bit_assembled_as_documented(ref):
+    for which, lo, hi, neg in (("exp_spread", 2.0 ** -6, 1024.0, True), ("log_spread", 2.0 ** -8, 256.0, False)):
+        a = ref.spread_args(which, 3, 1, 1 << 14)
+        assert ((a < 0) == neg).all()
+        m = np.abs(a)
+        assert m.min() >= lo and m.max() < hi
+        e = np.floor(np.log2(m)).astype(int)
+        counts = np.bincount(e - e.min(), minlength=16)
+        assert len(counts) == 16 and counts.min() > 0.7 * len(a) / 16       # 16 octaves, roughly uniform
+        assert (a.view(np.uint64) & np.uint64(0xFFFFFFFF) == 0).all()       # low word is zero

@@ -1,23 +1,22 @@
 #!/usr/bin/env bash
-# One gpurun call: GPU tests, bench line, ncu launch list, ncu --set full of the two main kernels.
-# Usage (from the repo root on the GPU box): bash tools/gpu_round.sh r01
+# One gpurun call on ONE GPU: GPU tests, bench line, ncu launch list, ncu --set full of the
+# LSE kernels (memory-fed and register-fed) and the world-1 step kernel.
+# Usage (from the repo root on the GPU box): bash tools/gpu_round.sh r02
 set -u
-tag=${1:-r01}
+tag=${1:-r02}
 out=gpurun_out
 mkdir -p $out
 nvidia-smi --query-gpu=name,driver_version,clocks.max.sm,clocks.max.mem,power.limit --format=csv > $out/${tag}_gpu.csv
-timeout 600 python -m pytest tests -m gpu -x -q -s > $out/${tag}_gpu_tests.log 2>&1
+timeout 900 python -m pytest tests -m gpu -x -q -s > $out/${tag}_gpu_tests.log 2>&1
 echo "pytest_exit=$?" >> $out/${tag}_gpu_tests.log
 timeout 300 python bench.py > $out/${tag}_bench.json 2> $out/${tag}_bench.err
 echo "bench_exit=$?" >> $out/${tag}_bench.err
 timeout 300 python bench.py --impl reference > $out/${tag}_bench_reference.json 2>&1
 # ncu only after the identical command exited 0 without it
 timeout 300 python bench.py --steps 3 --warmup 3 > $out/${tag}_plain.log 2>&1 &&
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv \
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
     --log-file $out/${tag}_launches.csv python bench.py --steps 3 --warmup 3 > $out/${tag}_ncu_launches.log 2>&1 &&
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:dfma_peak -s 3 -c 1 \
-    -o $out/${tag}_dfma python bench.py --steps 3 --warmup 3 > $out/${tag}_ncu_dfma.log 2>&1 &&
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:lse_rows -s 3 -c 1 \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'lse_kernel|vshard_step|shard_partials' -c 20 \
     -o $out/${tag}_lse python bench.py --steps 3 --warmup 3 > $out/${tag}_ncu_lse.log 2>&1
 echo "ncu_chain_exit=$?" > $out/${tag}_ncu_exit.txt
-tail -3 $out/${tag}_gpu_tests.log; cat $out/${tag}_bench.json; cat $out/${tag}_ncu_exit.txt
+tail -5 $out/${tag}_gpu_tests.log; cat $out/${tag}_bench.json; tail -3 $out/${tag}_bench.err; cat $out/${tag}_ncu_exit.txt
