@@ -34,23 +34,26 @@ using b9gw::Timer;
 // ---------------------------------------------------------------- DFMA peak
 // Each thread: ILP independent chains, fully unrolled; a and b arrive as kernel
 // arguments so nothing folds.  x0 depends on (chain, lane) only, so a CPU
-// checker needs 32*ILP chains, not one per thread.
+// checker needs 32*ILP chains, not one per thread.  ILP 8 is the peak measurement;
+// ILP 1/2/4 at one CTA per SM (two warps per scheduler) expose the dependent-issue
+// latency: with c chains in flight per scheduler the pipe retires c DFMAs per latency.
+template <int ILP>
 __global__ void __launch_bounds__(B9GW_DFMA_THREADS)
 dfma_peak_kernel(double *__restrict__ out, double a, double b, int iters) {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
-    double x[B9GW_DFMA_ILP];
+    double x[ILP];
 #pragma unroll
-    for (int j = 0; j < B9GW_DFMA_ILP; ++j)
+    for (int j = 0; j < ILP; ++j)
         x[j] = 1.0 + 0.125 * j + lane * 0x1p-10;
 #pragma unroll 4
     for (int i = 0; i < iters; ++i) {
 #pragma unroll
-        for (int j = 0; j < B9GW_DFMA_ILP; ++j) x[j] = fma(x[j], a, b);
+        for (int j = 0; j < ILP; ++j) x[j] = fma(x[j], a, b);
     }
     double s = x[0];
 #pragma unroll
-    for (int j = 1; j < B9GW_DFMA_ILP; ++j) s = __dadd_rn(s, x[j]);
+    for (int j = 1; j < ILP; ++j) s = __dadd_rn(s, x[j]);
     out[t] = s;
 }
 
@@ -123,6 +126,21 @@ __global__ void map_kernel(const double *__restrict__ x, double *__restrict__ y,
     for (; i < n; i += stride)
         y[i] = (WHICH == 0) ? exp(x[i]) : (WHICH == 1) ? log(x[i])
                : (WHICH == 2) ? exp10(x[i]) : log10(x[i]);
+}
+
+// The LSE kernel's branch-free copy of exp's fast path (common.cuh), on its own, so a
+// test can hold it against exp() bit for bit.  Only meaningful for -708 < x <= 0.
+__global__ void map_exp_fast_path_kernel(const __grid_constant__ b9gw::ExpConstants K,
+                                         const double *__restrict__ x, double *__restrict__ y,
+                                         long long n) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        const double in[1] = {x[i]};
+        double out[1];
+        b9gw::exp_fast_path(K, in, out);
+        y[i] = out[0];
+    }
 }
 
 __global__ void tick_kernel(double *out, double v) { *out = v; }
@@ -200,20 +218,27 @@ done:
     return rc;
 }
 
-int b9gw_dfma_peak(int device, int ctas_per_sm, int iters, double a, double b,
+int b9gw_dfma_peak(int device, int ctas_per_sm, int ilp, int iters, double a, double b,
                    int warmup, int reps, double *out_host, long long *n_threads,
                    float *ms_per_launch, double *tflops) {
     long long nthr = 0;
     float ms = 0.f;
+    if (ilp != 1 && ilp != 2 && ilp != 4 && ilp != 8) return fail(B9GW_E_ARG, "ilp must be 1, 2, 4 or 8");
     int rc = run_chain_bench(
         device, ctas_per_sm, iters, warmup, reps, out_host, &nthr, &ms,
         [=](int grid, cudaStream_t st, double *out) {
-            dfma_peak_kernel<<<grid, B9GW_DFMA_THREADS, 0, st>>>(out, a, b, iters);
+            constexpr int T = B9GW_DFMA_THREADS;
+            switch (ilp) {
+                case 1: dfma_peak_kernel<1><<<grid, T, 0, st>>>(out, a, b, iters); break;
+                case 2: dfma_peak_kernel<2><<<grid, T, 0, st>>>(out, a, b, iters); break;
+                case 4: dfma_peak_kernel<4><<<grid, T, 0, st>>>(out, a, b, iters); break;
+                default: dfma_peak_kernel<8><<<grid, T, 0, st>>>(out, a, b, iters);
+            }
         });
     if (rc != B9GW_OK) return rc;
     if (n_threads) *n_threads = nthr;
     if (ms_per_launch) *ms_per_launch = ms;
-    if (tflops) *tflops = 2.0 * B9GW_DFMA_ILP * (double)iters * (double)nthr / (ms * 1e-3) * 1e-12;
+    if (tflops) *tflops = 2.0 * ilp * (double)iters * (double)nthr / (ms * 1e-3) * 1e-12;
     return rc;
 }
 
@@ -313,7 +338,8 @@ done:
 int b9gw_map(int device, int which, const double *x_host, double *y_host, long long n) {
     int rc = B9GW_OK, sms = 0;
     double *dx = nullptr, *dy = nullptr;
-    if (which < 0 || which > 3) return fail(B9GW_E_ARG, "which must be 0 exp, 1 log, 2 exp10, 3 log10");
+    if (which < 0 || which > 4)
+        return fail(B9GW_E_ARG, "which must be 0 exp, 1 log, 2 exp10, 3 log10, 4 exp fast path");
     if (!b9gw::count_ok(n) || (n > 0 && (!x_host || !y_host)))
         return fail(B9GW_E_ARG, "null buffer, n<0 or n*8 overflows");
     b9gw::DeviceGuard guard(device);
@@ -327,7 +353,8 @@ int b9gw_map(int device, int which, const double *x_host, double *y_host, long l
         case 0: map_kernel<0><<<sms * 8, 256>>>(dx, dy, n); break;
         case 1: map_kernel<1><<<sms * 8, 256>>>(dx, dy, n); break;
         case 2: map_kernel<2><<<sms * 8, 256>>>(dx, dy, n); break;
-        default: map_kernel<3><<<sms * 8, 256>>>(dx, dy, n);
+        case 3: map_kernel<3><<<sms * 8, 256>>>(dx, dy, n); break;
+        default: map_exp_fast_path_kernel<<<sms * 8, 256>>>(b9gw::exp_constants(), dx, dy, n);
     }
     CK(cudaGetLastError());
     CK(cudaMemcpy(y_host, dy, n * sizeof(double), cudaMemcpyDeviceToHost));

@@ -1,31 +1,53 @@
-// lse.cu — fixed-order FP64 log-sum-exp over rows, for sm_100a.
+// lse.cu — fixed-order FP64 log-sum-exp over rows, and their sum over virtual
+// shards, for sm_100a.
 //
 // Reference-independent groundwork (the BASE-9 hot path is BLOCKED;
-// nothing here restates or imitates reference code).  One warp owns a row.  The
-// ORDER is the contract, pinned bit for bit by oracle/groundwork_ref.c:
-//   max   : exact, any order;
-//   sum   : lane l adds exp(x[c] - max) for c = l, l+32, l+64, ... in increasing
-//           c, starting from +0; the 32 lane sums are combined by an
-//           xor-butterfly with offsets 16, 8, 4, 2, 1;
-//   value : max + log(sum), or -inf when max == -inf;
-//   total : sum of the row values in the order of b9ref_ordered_sum.
-// Two term sources share that code: a matrix in memory (lse_rows) and a
-// closed-form generator evaluated in registers (lse_generated), so the second
-// shows what the fixed order costs when terms never travel through memory.
+// nothing here restates or imitates reference code).  The ORDER is the
+// contract, pinned bit for bit by oracle/groundwork_ref.c:
+//   max     : exact, any order;
+//   sum     : lane l adds exp(x[c] - max) for c = l, l+32, l+64, ... in
+//             increasing c, starting from +0; the 32 lane sums are combined by
+//             an xor-butterfly with offsets 16, 8, 4, 2, 1;
+//   value   : max + log(sum), or -inf when max == -inf;
+//   P[v]    : warp-order sum (same lane-strided + butterfly shape) of the row
+//             values of virtual shard v = rows [floor(v*R/V), floor((v+1)*R/V));
+//   total   : (((0 + P[0]) + P[1]) + ...) + P[V-1]  — the same definition the
+//             cross-rank sum uses (vshard.cu), so one kernel's P[] can feed it.
+//
+// The order says which lane ADDS which term; it does not say which thread
+// evaluates exp.  Staged rows (<= B9GW_LSE_STAGED_COLS columns) use that:
+//   pass 1  : the row's two warps fetch/generate every term once and park it
+//             in the row's slice of shared memory, tracking the max;
+//   pass 2a : the same 64 threads overwrite each parked term with
+//             exp(term - max) — independent work, any thread may do any term;
+//   pass 2b : one warp adds the parked exponentials in the pinned order.
+// Two warps per row double the exp chains in flight per staged row (shared
+// memory, 8 KB a row, is what limits rows in flight), which is what an
+// exp-latency-bound loop needs; profiles/r02_groundwork.md has the numbers for
+// the one-warp-per-row variants this replaced.
+// Two term sources share the code: a matrix in memory (lse_rows) and a
+// closed-form generator evaluated on chip (lse_generated).
 //
 // Every value-path operation is an explicit __dadd_rn/__dsub_rn/__dmul_rn/fma,
 // so -fmad cannot contract anything the host checker does not.
 
 #include <math.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 
 namespace {
 
 using b9gw::fail;
+using b9gw::ExpConstants;
+using b9gw::exp_constants;
+using b9gw::exp_fast_path;
 
-constexpr int LSE_WARPS = 8;              // rows per CTA
 constexpr unsigned FULL = 0xffffffffu;
+constexpr int CTA_THREADS = 256;
+constexpr int STAGED_WARPS = 4;           // staged rows in flight per CTA, one warp each
+constexpr int STREAM_ROWS = 8;            // rows per CTA, one warp each
 
 // ------------------------------------------------------------- term sources
 struct MatrixRow {                        // terms live in memory
@@ -35,15 +57,17 @@ struct MatrixRow {                        // terms live in memory
 
 struct GeneratedRow {                     // terms are arithmetic on (row, col)
     double w, b;                          // t = fma(c, w, b), term = -(t*t)
-    __device__ GeneratedRow(long long row, long long cols) {
-        const double colsd = (double)cols;
-        const double u = __dmul_rn((double)row, 0.6180339887498949);
-        const double c0 = __dmul_rn(__dsub_rn(u, floor(u)), colsd);
-        w = __ddiv_rn((double)(34 + (int)(row % 7)), colsd);
+    __device__ GeneratedRow(long long row, long long cols, double inv_cols) {
+        const unsigned r32 = (unsigned)row;                       // rows < 2^31 (checked by the host)
+        const double u = __dmul_rn((double)r32, 0.6180339887498949);
+        const double c0 = __dmul_rn(__dsub_rn(u, floor(u)), (double)cols);
+        w = __dmul_rn((double)(34u + r32 % 7u), inv_cols);        // inv_cols = 1.0 / cols, rounded once
         b = -__dmul_rn(c0, w);
     }
     __device__ double operator()(long long c) const {
-        const double t = fma((double)c, w, b);
+        // (double)c for 0 <= c < 2^52 as one exact DADD instead of a 64-bit I2F conversion
+        const double cd = __dsub_rn(__longlong_as_double(0x4330000000000000LL | c), 4503599627370496.0);
+        const double t = fma(cd, w, b);
         return __dmul_rn(-t, t);
     }
 };
@@ -60,176 +84,286 @@ __device__ __forceinline__ double warp_add(double s) {
     return s;
 }
 
-// Row of at most 32*TPL columns: every term is fetched/generated once, all of a
-// lane's TPL fetches are independent (loads in flight together), and the terms
-// stay in registers between the max pass and the exp pass.
-template <int TPL, class Src>
-__device__ __forceinline__ double warp_lse_regs(const Src &src, long long cols, int lane) {
-    double v[TPL];
-#pragma unroll
-    for (int k = 0; k < TPL; ++k) {
-        const long long c = lane + 32 * k;
-        v[k] = c < cols ? src(c) : -INFINITY;
-    }
-    double m = -INFINITY;
-#pragma unroll
-    for (int k = 0; k < TPL; ++k) m = fmax(m, v[k]);
-    m = warp_max(m);
-    if (m == -INFINITY) return -INFINITY;   // every term is exp(-inf) = 0 (also cols == 0)
+__device__ __forceinline__ long long shard_lo(long long n, int shift, long long v) {
+    return (long long)(((unsigned long long)v * (unsigned long long)n) >> shift);
+}
+
+// Lane-strided serial partials over v[lo..hi), 4 loads in flight, then the butterfly.
+__device__ __forceinline__ double warp_ordered_sum(const double *v, long long lo, long long hi, int lane) {
     double s = 0.0;
+    for (long long i0 = lo + lane; i0 < hi; i0 += 32 * 4) {
+        double x[4];
 #pragma unroll
-    for (int k = 0; k < TPL; ++k)
-        if (lane + 32 * k < cols) s = __dadd_rn(s, exp(__dsub_rn(v[k], m)));
-    return __dadd_rn(m, log(warp_add(s)));
+        for (int u = 0; u < 4; ++u) x[u] = i0 + 32 * u < hi ? __ldcg(v + i0 + 32 * u) : 0.0;
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (i0 + 32 * u < hi) s = __dadd_rn(s, x[u]);
+    }
+    return warp_add(s);
 }
 
-// Longer rows: two passes over the source, 8 independent fetches per lane at a time.
-template <class Src>
-__device__ __forceinline__ double warp_lse_stream(const Src &src, long long cols, int lane) {
-    constexpr int B = 8;
-    double m = -INFINITY;
-    for (long long c0 = lane; c0 < cols; c0 += 32 * B) {
-        double v[B];
-#pragma unroll
-        for (int k = 0; k < B; ++k) {
-            const long long c = c0 + 32 * k;
-            v[k] = c < cols ? src(c) : -INFINITY;
+__device__ __forceinline__ unsigned ticket_add(unsigned *p, unsigned v) {
+    unsigned old;                          // release our row values, acquire everyone else's
+    asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
+    return old;
+}
+
+// Called by one whole warp once the row values of rows [row0, row1) are stored — all of
+// them by this warp's lane 0, which also takes the tickets, so a ticket releases them.
+// The warp that completes a virtual shard adds that shard's row values; the warp that
+// completes the last shard adds the shards left to right.  Which warp that is does not
+// change any bit.  tickets[0..V-1] count finished rows per shard, tickets[V] finished
+// shards; each is reset by its last user, ready for the next launch on the stream.
+__device__ void finish_rows(long long row0, long long row1, long long rows, int vshift,
+                            double *row_lse, double *partials, double *total,
+                            unsigned *tickets, int lane) {
+    const int V = 1 << vshift;
+    const long long v0 = (((row0 + 1) << vshift) + rows - 1) / rows - 1;   // shard holding row0
+    bool all_done = false;
+    for (long long v = v0; v < V; ++v) {
+        const long long lo = shard_lo(rows, vshift, v), hi = shard_lo(rows, vshift, v + 1);
+        if (lo >= row1) break;
+        if (hi <= lo) continue;                            // empty shard (rows < V)
+        const unsigned mine = (unsigned)((hi < row1 ? hi : row1) - (lo > row0 ? lo : row0));
+        unsigned done = 0;
+        if (lane == 0) done = ticket_add(&tickets[v], mine) + mine == (unsigned)(hi - lo);
+        if (!__shfl_sync(FULL, done, 0)) continue;
+        __threadfence();
+        const double p = warp_ordered_sum(row_lse, lo, hi, lane);
+        done = 0;
+        if (lane == 0) {
+            partials[v] = p;
+            tickets[v] = 0;
+            const unsigned nonempty = rows < V ? (unsigned)rows : (unsigned)V;
+            done = ticket_add(&tickets[V], 1u) + 1u == nonempty;
         }
-#pragma unroll
-        for (int k = 0; k < B; ++k) m = fmax(m, v[k]);
+        all_done |= __shfl_sync(FULL, done, 0) != 0;
     }
-    m = warp_max(m);
-    if (m == -INFINITY) return -INFINITY;
-    double s = 0.0;
-    for (long long c0 = lane; c0 < cols; c0 += 32 * B) {
-        double v[B];
+    if (!all_done) return;
+    __threadfence();
+    double pk[B9GW_MAX_VSHARDS / 32];
 #pragma unroll
-        for (int k = 0; k < B; ++k) {
-            const long long c = c0 + 32 * k;
-            v[k] = c < cols ? src(c) : -INFINITY;
+    for (int k = 0; k < B9GW_MAX_VSHARDS / 32; ++k) {
+        const int u = lane + 32 * k;
+        pk[k] = 0.0;
+        if (u < V) {
+            if (shard_lo(rows, vshift, u + 1) > shard_lo(rows, vshift, u)) pk[k] = __ldcg(partials + u);
+            else partials[u] = 0.0;                        // an empty shard contributes +0
         }
-#pragma unroll
-        for (int k = 0; k < B; ++k)
-            if (c0 + 32 * k < cols) s = __dadd_rn(s, exp(__dsub_rn(v[k], m)));
     }
-    return __dadd_rn(m, log(warp_add(s)));
+    double acc = 0.0;
+#pragma unroll
+    for (int k = 0; k < B9GW_MAX_VSHARDS / 32; ++k)
+#pragma unroll 1
+        for (int u = 0; u < 32; ++u) {
+            const double pv = __shfl_sync(FULL, pk[k], u);
+            if (32 * k + u < V) acc = __dadd_rn(acc, pv);
+        }
+    if (lane == 0) {
+        *total = acc;
+        tickets[V] = 0;
+    }
 }
 
-// Fixed-order sum of n doubles by one CTA of 256 threads, in the order of
-// b9ref_ordered_sum: 1024 strided serial partials (thread t owns partials t,
-// t+256, t+512, t+768), then a pairwise tree over the 1024.
-__device__ double cta_ordered_sum(const double *v, long long n, double *p /* shared[1024] */) {
-    const int t = threadIdx.x;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        const int j = t + 256 * q;
-        double s = 0.0;
-        for (long long i = j; i < n; i += 1024) s = __dadd_rn(s, __ldcg(v + i));
-        p[j] = s;
-    }
-    __syncthreads();
-    for (int w = 512; w > 0; w >>= 1) {
-        for (int j = t; j < w; j += 256) p[j] = __dadd_rn(p[j], p[j + w]);
-        __syncthreads();
-    }
-    return p[0];
-}
+// Exact max without fmax's NaN fix-up: m is never NaN, and a NaN term compares false
+// either way, so this returns what fmax(m, v) would.
+__device__ __forceinline__ double max_keep(double m, double v) { return v > m ? v : m; }
 
-// SRC 0: matrix, 1: generator.  TPL 0 selects the streaming (two-pass) path.
-// The last CTA to retire adds the row values in the fixed order, so the total
-// needs no second launch; its order does not depend on which CTA that is.
-template <int SRC, int TPL>
-__global__ void __launch_bounds__(LSE_WARPS * 32)
-lse_kernel(const double *__restrict__ x, long long rows, long long cols,
-           double *__restrict__ row_lse, double *__restrict__ total,
-           unsigned *__restrict__ ticket) {
-    __shared__ double p[1024];
-    __shared__ bool last;
-    const int lane = threadIdx.x & 31;
-    const long long row = (long long)blockIdx.x * LSE_WARPS + (threadIdx.x >> 5);
-    if (row < rows) {                      // whole warp takes the same branch
-        double r;
-        if constexpr (SRC == 0) {
-            const MatrixRow src{x + row * cols};
-            if constexpr (TPL > 0) r = warp_lse_regs<TPL>(src, cols, lane);
-            else r = warp_lse_stream(src, cols, lane);
-        } else {
-            const GeneratedRow src(row, cols);
-            if constexpr (TPL > 0) r = warp_lse_regs<TPL>(src, cols, lane);
-            else r = warp_lse_stream(src, cols, lane);
+// Staged rows: one warp per row, STAGED_WARPS rows per CTA, `cap` doubles of shared memory
+// per row (cols rounded up to 128).  Pass 1 fetches/generates every term once and parks it;
+// pass 2 takes four parked terms per lane at a time: when all 128 of the warp's arguments
+// are inside libm's fast-path range the four exps run interleaved and branch-free,
+// otherwise the warp calls exp() itself.  Trip counts are warp-uniform; the padding columns
+// hold -inf, whose exp is +0 and changes no bit of the sum.
+template <int SRC>
+__global__ void __launch_bounds__(STAGED_WARPS * 32)
+lse_staged_kernel(const __grid_constant__ ExpConstants K, const double *__restrict__ x,
+                  long long rows, int n, int cap, int rpw,
+                  double inv_cols, int vshift, double *__restrict__ row_lse,
+                  double *__restrict__ partials, double *__restrict__ total,
+                  unsigned *__restrict__ tickets) {
+    extern __shared__ double sm[];        // [STAGED_WARPS][cap]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double *buf = sm + warp * cap + lane;
+    const int iters = cap >> 5;           // multiple of 4
+    const long long row0 = ((long long)blockIdx.x * STAGED_WARPS + warp) * rpw;
+    const long long row1 = row0 + rpw < rows ? row0 + rpw : rows;
+
+    for (long long row = row0; row < row1; ++row) {
+        // pass 1: fetch/generate once, park, max
+        double m = -INFINITY;
+        auto fetch = [&](auto src) {
+            if (n == cap) {               // no padding: no predicate (warp-uniform choice)
+#pragma unroll (SRC == 0 ? 8 : 4)
+                for (int k = 0; k < iters; ++k) {
+                    const double v = src(lane + 32 * k);
+                    buf[32 * k] = v;
+                    m = max_keep(m, v);
+                }
+            } else {
+#pragma unroll 4
+                for (int k = 0; k < iters; ++k) {
+                    const int c = lane + 32 * k;
+                    const double v = c < n ? src(c) : -INFINITY;
+                    buf[32 * k] = v;
+                    m = max_keep(m, v);
+                }
+            }
+        };
+        if constexpr (SRC == 0) fetch(MatrixRow{x + row * n});
+        else fetch(GeneratedRow(row, n, inv_cols));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = max_keep(m, __shfl_xor_sync(FULL, m, o));
+
+        double r = -INFINITY;             // every term is exp(-inf) = 0 (also n == 0)
+        if (m != -INFINITY) {             // warp-uniform
+            // pass 2: lane l adds exp(term - m) over c = l, l+32, ... in increasing c
+            double s = 0.0;
+            for (int k = 0; k < iters; k += 4) {
+                double d[4], e[4];
+                bool fast = true;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    d[i] = __dsub_rn(buf[32 * (k + i)], m);
+                    fast &= d[i] > -708.0;                 // false for NaN as well
+                }
+                if (__all_sync(FULL, fast)) {
+                    exp_fast_path(K, d, e);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) e[i] = exp(d[i]);
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) s = __dadd_rn(s, e[i]);
+            }
+            r = __dadd_rn(m, log(warp_add(s)));
         }
         if (lane == 0) row_lse[row] = r;
+        __syncwarp();                     // the row's slice is reused by the next row
     }
-    __threadfence();                       // row values visible before the ticket
-    __syncthreads();
-    if (threadIdx.x == 0) last = atomicAdd(ticket, 1u) == gridDim.x - 1;
-    __syncthreads();
-    if (!last) return;
-    __threadfence();
-    const double s = cta_ordered_sum(row_lse, rows, p);
-    if (threadIdx.x == 0) {
-        *total = s;
-        *ticket = 0;                       // ready for the next launch on this stream
-    }
+    if (row0 < row1) finish_rows(row0, row1, rows, vshift, row_lse, partials, total, tickets, lane);
+}
+
+// Longer rows: one warp per row, two passes over the source.
+template <int SRC>
+__global__ void __launch_bounds__(CTA_THREADS)
+lse_stream_kernel(const double *__restrict__ x, long long rows, long long cols, double inv_cols,
+                  int vshift, double *__restrict__ row_lse, double *__restrict__ partials,
+                  double *__restrict__ total, unsigned *__restrict__ tickets) {
+    const int lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * STREAM_ROWS + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    auto lse = [&](auto src) -> double {
+        constexpr int B = 8;
+        double m = -INFINITY;
+        for (long long c0 = lane; c0 < cols; c0 += 32 * B) {
+            double v[B];
+#pragma unroll
+            for (int k = 0; k < B; ++k) v[k] = c0 + 32 * k < cols ? src(c0 + 32 * k) : -INFINITY;
+#pragma unroll
+            for (int k = 0; k < B; ++k) m = fmax(m, v[k]);
+        }
+        m = warp_max(m);
+        if (m == -INFINITY) return -INFINITY;
+        double s = 0.0;
+#pragma unroll 4
+        for (long long c = lane; c < cols; c += 32) s = __dadd_rn(s, exp(__dsub_rn(src(c), m)));
+        return __dadd_rn(m, log(warp_add(s)));
+    };
+    double r;
+    if constexpr (SRC == 0) r = lse(MatrixRow{x + row * cols});
+    else r = lse(GeneratedRow(row, cols, inv_cols));
+    if (lane == 0) row_lse[row] = r;
+    finish_rows(row, row + 1, rows, vshift, row_lse, partials, total, tickets, lane);
 }
 
 __global__ void __launch_bounds__(256)
-generate_terms_kernel(double *__restrict__ x, long long rows, long long cols) {
+generate_terms_kernel(double *__restrict__ x, long long rows, long long cols, double inv_cols) {
     const long long n = rows * cols;
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (; i < n; i += stride) {
         const long long r = i / cols, c = i - r * cols;
-        x[i] = GeneratedRow(r, cols)(c);
+        x[i] = GeneratedRow(r, cols, inv_cols)(c);
     }
 }
 
-__global__ void zero_total_kernel(double *total) { *total = 0.0; }
+__global__ void no_rows_kernel(double *partials, int V, double *total) {   // the empty sum
+    for (int v = threadIdx.x; v < V; v += blockDim.x) partials[v] = 0.0;
+    if (threadIdx.x == 0) *total = 0.0;
+}
+
+inline int log2_of(int V) {
+    int s = 0;
+    while ((1 << s) < V) ++s;
+    return s;
+}
+
+int env_int(const char *name, int lo, int hi, int dflt) {   // tuning aids, not an interface
+    const char *e = getenv(name);
+    const int n = e ? atoi(e) : 0;
+    return n >= lo && n <= hi ? n : dflt;
+}
+
+// Rows a staged warp takes in sequence (amortises the ticket round trip that ends its work).
+int rows_per_warp() {
+    static int v = env_int("B9GW_LSE_ROWS_PER_WARP", 1, 64, 2);
+    return v;
+}
 
 template <int SRC>
-void launch_lse(unsigned grid, cudaStream_t st, const double *x, long long rows, long long cols,
-                double *row_lse, double *total, unsigned *ticket) {
-    constexpr int T = LSE_WARPS * 32;
-    if (cols <= 128)
-        lse_kernel<SRC, 4><<<grid, T, 0, st>>>(x, rows, cols, row_lse, total, ticket);
-    else if (cols <= 512)
-        lse_kernel<SRC, 16><<<grid, T, 0, st>>>(x, rows, cols, row_lse, total, ticket);
-    else if (cols <= B9GW_LSE_REG_COLS)
-        lse_kernel<SRC, 32><<<grid, T, 0, st>>>(x, rows, cols, row_lse, total, ticket);
-    else
-        lse_kernel<SRC, 0><<<grid, T, 0, st>>>(x, rows, cols, row_lse, total, ticket);
+cudaError_t launch_lse(cudaStream_t st, const double *x, long long rows, long long cols, int V,
+                       double *row_lse, double *partials, double *total, unsigned *tickets) {
+    const double inv_cols = cols > 0 ? 1.0 / (double)cols : 0.0;
+    if (rows == 0) {
+        no_rows_kernel<<<1, 128, 0, st>>>(partials, V, total);
+    } else if (cols <= B9GW_LSE_STAGED_COLS) {
+        const int cap = (int)((cols + 127) / 128 * 128), rpw = rows_per_warp();
+        const long long per_cta = (long long)STAGED_WARPS * rpw;
+        const unsigned grid = (unsigned)((rows + per_cta - 1) / per_cta);
+        lse_staged_kernel<SRC><<<grid, STAGED_WARPS * 32, sizeof(double) * STAGED_WARPS * cap, st>>>(
+            exp_constants(), x, rows, (int)cols, cap, rpw, inv_cols, log2_of(V), row_lse, partials,
+            total, tickets);
+    } else {
+        const unsigned grid = (unsigned)((rows + STREAM_ROWS - 1) / STREAM_ROWS);
+        lse_stream_kernel<SRC><<<grid, CTA_THREADS, 0, st>>>(x, rows, cols, inv_cols, log2_of(V),
+                                                            row_lse, partials, total, tickets);
+    }
+    return cudaGetLastError();
 }
 
 // Shared host body: SRC 0 uploads x_host, SRC 1 has no input at all.
 template <int SRC>
-int run_lse(int device, const double *x_host, long long rows, long long cols, int warmup, int reps,
-            double *row_lse_host, double *total_host, float *ms_per_launch) {
+int run_lse(int device, const double *x_host, long long rows, long long cols, int V, int warmup,
+            int reps, double *row_lse_host, double *partials_host, double *total_host,
+            float *ms_per_launch) {
     int rc = B9GW_OK;
-    double *dx = nullptr, *dr = nullptr, *dt = nullptr;
-    unsigned *dticket = nullptr;
+    double *dx = nullptr, *dr = nullptr, *dp = nullptr, *dt = nullptr;
+    unsigned *dtickets = nullptr;
     cudaStream_t st = nullptr;
     b9gw::Timer tm;
     float ms = 0.f;
     if (rows < 0 || cols < 0 || warmup < 0 || reps < 1)
         return fail(B9GW_E_ARG, "need rows>=0, cols>=0, warmup>=0, reps>=1");
-    if (!b9gw::product_ok(rows, cols) || !b9gw::count_ok(rows))
-        return fail(B9GW_E_ARG, "rows*cols overflows");
+    if (V < 4 || V > B9GW_MAX_VSHARDS || (V & (V - 1)))
+        return fail(B9GW_E_ARG, "n_vshards must be a power of two in [4,128]");
+    if (!b9gw::product_ok(rows, cols) || rows > (1LL << 31) - 1 || cols > (1LL << 40))
+        return fail(B9GW_E_ARG, "rows*cols overflows (or rows > 2^31-1, cols > 2^40)");
     if (SRC == 0 && rows * cols > 0 && !x_host) return fail(B9GW_E_ARG, "x_host is null");
     if (!total_host) return fail(B9GW_E_ARG, "total_host is null");
-    if ((rows + LSE_WARPS - 1) / LSE_WARPS > 0x7fffffffLL) return fail(B9GW_E_ARG, "too many rows");
     b9gw::DeviceGuard guard(device);
     if (guard.rc() != B9GW_OK) return guard.rc();
     {
         const long long n = rows * cols;
-        const unsigned grid = (unsigned)((rows + LSE_WARPS - 1) / LSE_WARPS);
         if (SRC == 0) {
             CK(cudaMalloc(&dx, (n > 0 ? n : 1) * sizeof(double)));
             if (n > 0) CK(cudaMemcpy(dx, x_host, n * sizeof(double), cudaMemcpyHostToDevice));
         }
         CK(cudaMalloc(&dr, (rows > 0 ? rows : 1) * sizeof(double)));
+        CK(cudaMalloc(&dp, V * sizeof(double)));
         CK(cudaMalloc(&dt, sizeof(double)));
-        CK(cudaMalloc(&dticket, sizeof(unsigned)));
-        CK(cudaMemset(dticket, 0, sizeof(unsigned)));
+        CK(cudaMalloc(&dtickets, (V + 1) * sizeof(unsigned)));
+        CK(cudaMemset(dtickets, 0, (V + 1) * sizeof(unsigned)));
         CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
         CK(tm.init());
         for (int i = 0; i < warmup + reps; ++i) {
@@ -237,17 +371,14 @@ int run_lse(int device, const double *x_host, long long rows, long long cols, in
                 CK(cudaStreamSynchronize(st));
                 CK(cudaEventRecord(tm.a, st));
             }
-            if (grid > 0)
-                launch_lse<SRC>(grid, st, dx, rows, cols, dr, dt, dticket);
-            else
-                zero_total_kernel<<<1, 1, 0, st>>>(dt);   // no rows: the empty sum
+            CK(launch_lse<SRC>(st, dx, rows, cols, V, dr, dp, dt, dtickets));
         }
         CK(cudaEventRecord(tm.b, st));
-        CK(cudaGetLastError());
         CK(cudaStreamSynchronize(st));
         CK(cudaEventElapsedTime(&ms, tm.a, tm.b));
         if (row_lse_host && rows > 0)
             CK(cudaMemcpy(row_lse_host, dr, rows * sizeof(double), cudaMemcpyDeviceToHost));
+        if (partials_host) CK(cudaMemcpy(partials_host, dp, V * sizeof(double), cudaMemcpyDeviceToHost));
         CK(cudaMemcpy(total_host, dt, sizeof(double), cudaMemcpyDeviceToHost));
     }
     if (ms_per_launch) *ms_per_launch = ms / reps;
@@ -255,8 +386,9 @@ done:
     if (st) cudaStreamDestroy(st);
     if (dx) cudaFree(dx);
     if (dr) cudaFree(dr);
+    if (dp) cudaFree(dp);
     if (dt) cudaFree(dt);
-    if (dticket) cudaFree(dticket);
+    if (dtickets) cudaFree(dtickets);
     return rc;
 }
 
@@ -264,31 +396,32 @@ done:
 
 extern "C" {
 
-int b9gw_lse_rows(int device, const double *x_host, long long rows, long long cols,
-                  int warmup, int reps, double *row_lse_host, double *total_host,
-                  float *ms_per_launch) {
-    return run_lse<0>(device, x_host, rows, cols, warmup, reps, row_lse_host, total_host,
-                      ms_per_launch);
+int b9gw_lse_rows(int device, const double *x_host, long long rows, long long cols, int n_vshards,
+                  int warmup, int reps, double *row_lse_host, double *partials_host,
+                  double *total_host, float *ms_per_launch) {
+    return run_lse<0>(device, x_host, rows, cols, n_vshards, warmup, reps, row_lse_host,
+                      partials_host, total_host, ms_per_launch);
 }
 
-int b9gw_lse_generated(int device, long long rows, long long cols, int warmup, int reps,
-                       double *row_lse_host, double *total_host, float *ms_per_launch) {
-    return run_lse<1>(device, nullptr, rows, cols, warmup, reps, row_lse_host, total_host,
-                      ms_per_launch);
+int b9gw_lse_generated(int device, long long rows, long long cols, int n_vshards, int warmup,
+                       int reps, double *row_lse_host, double *partials_host, double *total_host,
+                       float *ms_per_launch) {
+    return run_lse<1>(device, nullptr, rows, cols, n_vshards, warmup, reps, row_lse_host,
+                      partials_host, total_host, ms_per_launch);
 }
 
 int b9gw_generate_terms(int device, long long rows, long long cols, double *x_host) {
     int rc = B9GW_OK, sms = 0;
     double *dx = nullptr;
-    if (rows < 0 || cols < 0 || !b9gw::product_ok(rows, cols))
-        return fail(B9GW_E_ARG, "need rows>=0, cols>=0 and rows*cols representable");
+    if (rows < 0 || cols < 0 || !b9gw::product_ok(rows, cols) || cols > (1LL << 40))
+        return fail(B9GW_E_ARG, "need rows>=0, 0<=cols<=2^40 and rows*cols representable");
     if (rows * cols > 0 && !x_host) return fail(B9GW_E_ARG, "x_host is null");
     b9gw::DeviceGuard guard(device);
     if (guard.rc() != B9GW_OK) return guard.rc();
     if (rows * cols == 0) return B9GW_OK;
     if ((rc = b9gw::sm_count_of(device, &sms)) != B9GW_OK) return rc;
     CK(cudaMalloc(&dx, rows * cols * sizeof(double)));
-    generate_terms_kernel<<<sms * 8, 256>>>(dx, rows, cols);
+    generate_terms_kernel<<<sms * 8, 256>>>(dx, rows, cols, 1.0 / (double)cols);
     CK(cudaGetLastError());
     CK(cudaMemcpy(x_host, dx, rows * cols * sizeof(double), cudaMemcpyDeviceToHost));
 done:

@@ -150,26 +150,40 @@ vshard_step_kernel(const StepArgs a) {
     if (threadIdx.x == 0) a.seq[blockIdx.x] = step;
 }
 
-__host__ __device__ inline long long shard_lo(long long n, int V, int v) {
-    return (long long)(((__int128)v * n) / V);
+// floor(v*n/V) for V a power of two (shift = log2 V), v <= V <= 128 and n <= 2^48: fits 64 bits.
+constexpr long long MAX_STARS = 1LL << 48;
+__host__ __device__ inline long long shard_lo(long long n, int shift, int v) {
+    return (long long)(((unsigned long long)v * (unsigned long long)n) >> shift);
+}
+inline int log2_of(int V) {
+    int s = 0;
+    while ((1 << s) < V) ++s;
+    return s;
 }
 
 // P[k][chain] for local shards k = 0 .. n_shards-1: one warp per (k, chain), warp order.
 __global__ void __launch_bounds__(PART_WARPS * 32)
 shard_partials_kernel(const double *__restrict__ values, long long chains, long long ld,
-                      long long n_total, int V, int first_shard, int n_shards,
+                      long long n_total, int vshift, int first_shard, int n_shards,
                       double *__restrict__ partial) {
     const int lane = threadIdx.x & 31;
     const long long w = (long long)blockIdx.x * PART_WARPS + (threadIdx.x >> 5);
     if (w >= (long long)n_shards * chains) return;      // whole warp
     const int k = (int)(w / chains);
     const long long chain = w - (long long)k * chains;
-    const long long base = shard_lo(n_total, V, first_shard);
-    const long long lo = shard_lo(n_total, V, first_shard + k) - base;
-    const long long hi = shard_lo(n_total, V, first_shard + k + 1) - base;
+    const long long base = shard_lo(n_total, vshift, first_shard);
+    const long long lo = shard_lo(n_total, vshift, first_shard + k) - base;
+    const long long hi = shard_lo(n_total, vshift, first_shard + k + 1) - base;
     const double *row = values + chain * ld;
     double s = 0.0;
-    for (long long i = lo + lane; i < hi; i += 32) s = __dadd_rn(s, __ldg(row + i));
+    for (long long i0 = lo + lane; i0 < hi; i0 += 32 * 4) {     // 4 loads in flight, adds in order
+        double x[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) x[u] = i0 + 32 * u < hi ? __ldg(row + i0 + 32 * u) : 0.0;
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (i0 + 32 * u < hi) s = __dadd_rn(s, x[u]);
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s = __dadd_rn(s, __shfl_xor_sync(FULL, s, o));
     if (lane == 0) partial[(long long)k * chains + chain] = s;
@@ -227,7 +241,7 @@ int launch_partials(const double *values_dev, long long chains, long long ld, lo
     const long long grid = (warps + PART_WARPS - 1) / PART_WARPS;
     if (grid > 0x7fffffffLL) return fail(B9GW_E_ARG, "n_shards*chains too large for one launch");
     shard_partials_kernel<<<(unsigned)grid, PART_WARPS * 32, 0, st>>>(
-        values_dev, chains, ld, n_total, V, first_shard, n_shards, partial_dev);
+        values_dev, chains, ld, n_total, log2_of(V), first_shard, n_shards, partial_dev);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(B9GW_E_CUDA, "shard_partials_kernel launch", e);
     return B9GW_OK;
@@ -238,10 +252,10 @@ int launch_partials(const double *values_dev, long long chains, long long ld, lo
 extern "C" {
 
 int b9gw_vshard_bounds(long long n_stars, int n_vshards, int shard, long long *lo, long long *hi) {
-    if (!vshards_ok(n_vshards) || shard < 0 || shard >= n_vshards || !b9gw::count_ok(n_stars))
-        return fail(B9GW_E_ARG, "need a power-of-two shard count in [4,128], 0<=shard<V, n_stars>=0");
-    if (lo) *lo = shard_lo(n_stars, n_vshards, shard);
-    if (hi) *hi = shard_lo(n_stars, n_vshards, shard + 1);
+    if (!vshards_ok(n_vshards) || shard < 0 || shard >= n_vshards || n_stars < 0 || n_stars > MAX_STARS)
+        return fail(B9GW_E_ARG, "need a power-of-two shard count in [4,128], 0<=shard<V, 0<=n_stars<=2^48");
+    if (lo) *lo = shard_lo(n_stars, log2_of(n_vshards), shard);
+    if (hi) *hi = shard_lo(n_stars, log2_of(n_vshards), shard + 1);
     return B9GW_OK;
 }
 
@@ -251,11 +265,12 @@ int b9gw_shard_partials(const double *values_dev, long long chains, long long ld
     if (!vshards_ok(n_vshards) || first_shard < 0 || n_shards < 0 ||
         first_shard + n_shards > n_vshards)
         return fail(B9GW_E_ARG, "bad shard range");
-    if (chains < 0 || chains > MAX_CHAINS || ld < 0 || !b9gw::count_ok(n_stars_total) ||
-        !b9gw::product_ok(chains, ld))
+    if (chains < 0 || chains > MAX_CHAINS || ld < 0 || n_stars_total < 0 ||
+        n_stars_total > MAX_STARS || !b9gw::product_ok(chains, ld))
         return fail(B9GW_E_ARG, "bad chains / ld / n_stars_total");
-    const long long n_local = shard_lo(n_stars_total, n_vshards, first_shard + n_shards) -
-                              shard_lo(n_stars_total, n_vshards, first_shard);
+    const int sh = log2_of(n_vshards);
+    const long long n_local = shard_lo(n_stars_total, sh, first_shard + n_shards) -
+                              shard_lo(n_stars_total, sh, first_shard);
     if (ld < n_local) return fail(B9GW_E_ARG, "ld is smaller than the local star count");
     if ((long long)n_shards * chains > 0 && (!partial_dev || (n_local > 0 && !values_dev)))
         return fail(B9GW_E_ARG, "null device buffer");
@@ -465,7 +480,7 @@ int b9gw_vshard_total(int device, const double *values_host, long long chains, l
     b9gw_comm *c = nullptr;
     char handle[B9GW_IPC_HANDLE_BYTES];
     if (!vshards_ok(n_vshards)) return fail(B9GW_E_ARG, "n_vshards must be a power of two in [4,128]");
-    if (chains < 0 || chains > MAX_CHAINS || !b9gw::count_ok(n_stars) ||
+    if (chains < 0 || chains > MAX_CHAINS || n_stars < 0 || n_stars > MAX_STARS ||
         !b9gw::product_ok(chains, n_stars))
         return fail(B9GW_E_ARG, "bad chains / n_stars");
     if (chains > 0 && (!total_host || (n_stars > 0 && !values_host)))

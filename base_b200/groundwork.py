@@ -15,7 +15,7 @@ import numpy as np
 LIB_PATH = Path(__file__).resolve().parent / "libb9_groundwork.so"
 ABI_VERSION = 3
 DFMA_ILP, TRANS_ILP, THREADS = 8, 4, 256
-LSE_REG_COLS, MAX_WORLD, MAX_VSHARDS, IPC_HANDLE_BYTES = 1024, 16, 128, 64
+LSE_STAGED_COLS, MAX_WORLD, MAX_VSHARDS, IPC_HANDLE_BYTES = 1024, 16, 128, 64
 E_NODEVICE, E_CUDA, E_ARG, E_TIMEOUT, E_STATE = -1, -2, -3, -4, -5
 
 # every symbol include/b9_groundwork.h declares: name -> (restype, argtypes)
@@ -27,13 +27,13 @@ SYMBOLS = {
     "b9gw_last_error": (C.c_char_p, []),
     "b9gw_device_count": (_i, []),
     "b9gw_device_info": (_i, [_i, _pi, _pi, _pll]),
-    "b9gw_dfma_peak": (_i, [_i, _i, _i, _d, _d, _i, _i, _pd, _pll, _pf, _pd]),
+    "b9gw_dfma_peak": (_i, [_i, _i, _i, _i, _d, _d, _i, _i, _pd, _pll, _pf, _pd]),
     "b9gw_transcendental_rate": (_i, [_i, _i, _i, _i, _i, _i, _pd, _pll, _pf, _pd]),
     "b9gw_step_latency": (_i, [_i, _i, _i, _pf, _pf, _pf]),
     "b9gw_map": (_i, [_i, _i, _pd, _pd, _ll]),
-    "b9gw_lse_rows": (_i, [_i, _pd, _ll, _ll, _i, _i, _pd, _pd, _pf]),
+    "b9gw_lse_rows": (_i, [_i, _pd, _ll, _ll, _i, _i, _i, _pd, _pd, _pd, _pf]),
     "b9gw_generate_terms": (_i, [_i, _ll, _ll, _pd]),
-    "b9gw_lse_generated": (_i, [_i, _ll, _ll, _i, _i, _pd, _pd, _pf]),
+    "b9gw_lse_generated": (_i, [_i, _ll, _ll, _i, _i, _i, _pd, _pd, _pd, _pf]),
     "b9gw_vshard_bounds": (_i, [_ll, _i, _i, _pll, _pll]),
     # *_dev arguments are raw device addresses (c_void_p), e.g. torch.Tensor.data_ptr()
     "b9gw_shard_partials": (_i, [_vp, _ll, _ll, _ll, _i, _i, _i, _vp, _vp]),
@@ -94,19 +94,19 @@ def device_info(device: int = 0) -> dict:
 
 
 def dfma_peak(device=0, ctas_per_sm=8, iters=1 << 16, a=1.0 - 2.0 ** -12, b=2.0 ** -12,
-              warmup=3, reps=10, want_out=False) -> dict:
+              warmup=3, reps=10, want_out=False, ilp=DFMA_ILP) -> dict:
     n, ms, tf = _ll(), _f(), _d()
     out = None
     if want_out:
         out = np.empty(device_info(device)["sm_count"] * ctas_per_sm * THREADS, dtype=np.float64)
-    _ck(lib().b9gw_dfma_peak(device, ctas_per_sm, iters, a, b, warmup, reps, _ptr(out),
+    _ck(lib().b9gw_dfma_peak(device, ctas_per_sm, ilp, iters, a, b, warmup, reps, _ptr(out),
                              C.byref(n), C.byref(ms), C.byref(tf)))
     return {"n_threads": n.value, "ms_per_launch": ms.value, "tflops": tf.value, "out": out,
-            "iters": iters, "ctas_per_sm": ctas_per_sm, "launches": warmup + reps}
+            "iters": iters, "ctas_per_sm": ctas_per_sm, "ilp": ilp, "launches": warmup + reps}
 
 
 TRANS_WHICH = {"exp": 0, "log": 1, "exp10": 2, "log10": 3, "exp_spread": 4, "log_spread": 5}
-MAP_WHICH = {"exp": 0, "log": 1, "exp10": 2, "log10": 3}
+MAP_WHICH = {"exp": 0, "log": 1, "exp10": 2, "log10": 3, "exp_fast_path": 4}
 
 
 def transcendental_rate(which: str, device=0, ctas_per_sm=8, iters=1 << 12, warmup=3, reps=10,
@@ -136,17 +136,18 @@ def device_map(which: str, x: np.ndarray, device=0) -> np.ndarray:
     return y
 
 
-def lse_rows(x: np.ndarray, device=0, warmup=0, reps=1) -> dict:
+def lse_rows(x: np.ndarray, device=0, warmup=0, reps=1, n_vshards=64) -> dict:
     x = np.ascontiguousarray(x, dtype=np.float64)
     if x.ndim != 2:
         raise ValueError("x must be rows x cols")
     rows, cols = x.shape
     row_lse = np.empty(rows, dtype=np.float64)
+    partials = np.empty(n_vshards, dtype=np.float64)
     total, ms = _d(), _f()
-    _ck(lib().b9gw_lse_rows(device, _ptr(x), rows, cols, warmup, reps, _ptr(row_lse),
-                            C.byref(total), C.byref(ms)))
-    return {"row_lse": row_lse, "total": total.value, "ms_per_launch": ms.value,
-            "launches": warmup + reps}
+    _ck(lib().b9gw_lse_rows(device, _ptr(x), rows, cols, n_vshards, warmup, reps, _ptr(row_lse),
+                            _ptr(partials), C.byref(total), C.byref(ms)))
+    return {"row_lse": row_lse, "partials": partials, "total": total.value,
+            "ms_per_launch": ms.value, "launches": warmup + reps}
 
 
 def generate_terms(rows: int, cols: int, device=0) -> np.ndarray:
@@ -155,13 +156,14 @@ def generate_terms(rows: int, cols: int, device=0) -> np.ndarray:
     return x
 
 
-def lse_generated(rows: int, cols: int, device=0, warmup=0, reps=1) -> dict:
+def lse_generated(rows: int, cols: int, device=0, warmup=0, reps=1, n_vshards=64) -> dict:
     row_lse = np.empty(rows, dtype=np.float64)
+    partials = np.empty(n_vshards, dtype=np.float64)
     total, ms = _d(), _f()
-    _ck(lib().b9gw_lse_generated(device, rows, cols, warmup, reps, _ptr(row_lse), C.byref(total),
-                                 C.byref(ms)))
-    return {"row_lse": row_lse, "total": total.value, "ms_per_launch": ms.value,
-            "launches": warmup + reps}
+    _ck(lib().b9gw_lse_generated(device, rows, cols, n_vshards, warmup, reps, _ptr(row_lse),
+                                 _ptr(partials), C.byref(total), C.byref(ms)))
+    return {"row_lse": row_lse, "partials": partials, "total": total.value,
+            "ms_per_launch": ms.value, "launches": warmup + reps}
 
 
 def vshard_bounds(n_stars: int, n_vshards: int, shard: int) -> tuple[int, int]:

@@ -45,11 +45,11 @@ extern "C" {
 #define B9GW_E_TIMEOUT   (-4)   /* a peer did not arrive within the comm's timeout */
 #define B9GW_E_STATE     (-5)   /* call made in the wrong state (e.g. not connected) */
 
-#define B9GW_DFMA_ILP      8    /* independent FMA chains per thread */
+#define B9GW_DFMA_ILP      8    /* independent FMA chains per thread at the peak (ilp = 8) */
 #define B9GW_DFMA_THREADS  256  /* threads per CTA */
 #define B9GW_TRANS_ILP     4    /* independent exp/log chains per thread */
 
-#define B9GW_LSE_REG_COLS  1024 /* rows up to this length stay in registers */
+#define B9GW_LSE_STAGED_COLS 1024 /* rows up to this length are staged on chip */
 
 #define B9GW_MAX_WORLD        16  /* ranks in one comm (one NVSwitch domain) */
 #define B9GW_MAX_VSHARDS      128 /* virtual shards; must be one of 4,8,16,32,64,128 */
@@ -71,17 +71,21 @@ int b9gw_device_info(int device, int *sm_count, int *sm_clock_mhz,
 /* ------------------------------------------------------------------ rates */
 
 /*
- * FP64 FMA peak.  Launches sm_count*ctas_per_sm CTAs of B9GW_DFMA_THREADS
- * threads; every thread advances B9GW_DFMA_ILP chains x <- fma(x, a, b) for
- * `iters` steps and stores the in-order sum of its chains.  Does `warmup`
- * untimed launches, then `reps` timed ones bracketed by CUDA events on the
- * launching stream.
+ * FP64 FMA peak and dependent-issue latency.  Launches sm_count*ctas_per_sm CTAs
+ * of B9GW_DFMA_THREADS threads; every thread advances `ilp` (1, 2, 4 or 8)
+ * independent chains x <- fma(x, a, b) for `iters` steps and stores the in-order
+ * sum of its chains.  ilp = 8 measures the peak.  ilp = 1 with ctas_per_sm = 1
+ * leaves two chains in flight per scheduler, so the time per step is half the
+ * dependent-issue latency: the number a design needs to know how many
+ * independent FP64 chains it must keep in flight.  Does `warmup` untimed
+ * launches, then `reps` timed ones bracketed by CUDA events on the launching
+ * stream.
  *   out_host   : n_threads doubles (may be NULL) — thread t's result depends
  *                only on (t & 31); see oracle/groundwork_ref.c:b9ref_dfma_lane
  *   n_threads  : total threads launched
- *   ms_per_launch, tflops : average over `reps`; flops = 2*ILP*iters*n_threads
+ *   ms_per_launch, tflops : average over `reps`; flops = 2*ilp*iters*n_threads
  */
-int b9gw_dfma_peak(int device, int ctas_per_sm, int iters, double a, double b,
+int b9gw_dfma_peak(int device, int ctas_per_sm, int ilp, int iters, double a, double b,
                    int warmup, int reps, double *out_host,
                    long long *n_threads, float *ms_per_launch, double *tflops);
 
@@ -119,53 +123,62 @@ int b9gw_step_latency(int device, int warmup, int reps, float *us_launch_sync,
                       float *us_launch_d2h_sync, float *us_graph_d2h_sync);
 
 /* Elementwise y[i] = f(x[i]) on the device, f = exp (which 0), log (1),
- * exp10 (2), log10 (3), for comparing CUDA libm with the host's bit by bit. */
+ * exp10 (2), log10 (3), for comparing CUDA libm with the host's bit by bit;
+ * which 4 is the LSE kernels' branch-free copy of exp's fast path, defined only
+ * for -708 < x <= 0 and required to equal exp there bit for bit. */
 int b9gw_map(int device, int which, const double *x_host, double *y_host,
              long long n);
 
 /* ------------------------------------------------- fixed-order log-sum-exp */
 
 /*
- * Fixed-order log-sum-exp.  x is rows x cols, row-major.  One warp per row:
- * exact row max, then each lane sums exp(x - max) over its columns
- * (col = lane, lane+32, ...) in increasing order, then an xor-butterfly
- * (offsets 16,8,4,2,1) adds the 32 partials; row_lse = max + log(sum), and
- * -inf for a row whose max is -inf.  `total` is the sum of row_lse in the fixed
- * order of b9ref_ordered_sum (1024 strided partials, then a pairwise tree).
- * Rows of up to B9GW_LSE_REG_COLS columns are read from memory ONCE, with all
- * of a lane's loads in flight together, and kept in registers between the max
- * pass and the exp pass; longer rows are read twice.  The order, and therefore
- * every bit of the result, is the same on both paths.
- * Timing covers `reps` launches of both kernels with x already on the device.
- *   row_lse_host : rows doubles (may be NULL);  total_host : 1 double
+ * Fixed-order log-sum-exp of every row, and the rows' sum over virtual shards.
+ * x is rows x cols, row-major.
+ *   row value : exact row max m; lane l (of 32) adds exp(x[c] - m) over its
+ *               columns c = l, l+32, ... in increasing order starting from +0;
+ *               an xor-butterfly (offsets 16,8,4,2,1) adds the 32 lane sums;
+ *               value = m + log(sum), and -inf for a row whose max is -inf.
+ *   P[v]      : the rows are cut into n_vshards virtual shards exactly as stars
+ *               are below ("world-size-independent sum"); P[v] is the warp-order
+ *               sum of shard v's row values (+0 for an empty shard).
+ *   total     : (((0 + P[0]) + P[1]) + ...) + P[V-1].
+ * The order fixes which lane ADDS which term, not which thread evaluates exp:
+ * rows of up to B9GW_LSE_STAGED_COLS columns are read from memory ONCE, parked
+ * in shared memory, exponentiated in place by two warps and then added in the
+ * pinned order by one; longer rows are read twice by one warp.  Every bit of the
+ * result is the same on both paths.  P[] and total are produced in the same
+ * launch, by whichever warp finishes a shard / the last shard.
+ * Timing covers `reps` launches with x already on the device.
+ *   row_lse_host : rows doubles (may be NULL);  partials_host : n_vshards
+ *   doubles (may be NULL);  total_host : 1 double
  */
 int b9gw_lse_rows(int device, const double *x_host, long long rows,
-                  long long cols, int warmup, int reps, double *row_lse_host,
+                  long long cols, int n_vshards, int warmup, int reps,
+                  double *row_lse_host, double *partials_host,
                   double *total_host, float *ms_per_launch);
 
 /*
  * The synthetic term generator, materialised: x[r*cols + c] = g(r, c, cols),
  *   u  = r * 0.6180339887498949,  c0 = (u - floor(u)) * cols,
- *   w  = (34 + (r mod 7)) / cols,
+ *   w  = (34 + (r mod 7)) * (1 / cols),
  *   t  = fma(c, w, -(c0 * w)),    g = -(t * t)
  * (each operation rounded once, as written; oracle/groundwork_ref.c:b9ref_gen_term
  * is the host statement).  A row is a parabola with its maximum (0 >= g > -1)
  * near column c0 and a minimum between about -290 and -1600: some rows reach
- * past exp's underflow threshold, all rows have a handful of terms near the
+ * past exp's underflow threshold, all rows have a few hundred terms near the
  * maximum that carry the sum.  It is arithmetic chosen to give exp a realistic
- * spread of arguments; it models nothing.
+ * spread of arguments; it models nothing.  cols <= 2^40.
  */
 int b9gw_generate_terms(int device, long long rows, long long cols, double *x_host);
 
 /*
- * The same fixed-order log-sum-exp, but every term is produced in registers by
- * g(r, c, cols) above: no matrix exists in memory, one exp per term.  Row
- * values and total are bit-identical to b9gw_lse_rows run on
- * b9gw_generate_terms' output.  Rows of up to B9GW_LSE_REG_COLS columns keep
- * their terms in registers between the two passes; longer rows regenerate them.
+ * The same computation, but every term is produced on chip by g(r, c, cols)
+ * above: no matrix exists in memory, one exp per term.  Row values, P[] and
+ * total are bit-identical to b9gw_lse_rows run on b9gw_generate_terms' output.
  */
-int b9gw_lse_generated(int device, long long rows, long long cols, int warmup,
-                       int reps, double *row_lse_host, double *total_host,
+int b9gw_lse_generated(int device, long long rows, long long cols, int n_vshards,
+                       int warmup, int reps, double *row_lse_host,
+                       double *partials_host, double *total_host,
                        float *ms_per_launch);
 
 /* -------------------------- world-size-independent sum over virtual shards */
@@ -183,7 +196,7 @@ int b9gw_lse_generated(int device, long long rows, long long cols, int warmup,
  * have this property — the grouping changes with W.)
  */
 
-/* Stars [lo, hi) of virtual shard `shard`.  Pure host arithmetic. */
+/* Stars [lo, hi) of virtual shard `shard`.  Pure host arithmetic.  n_stars <= 2^48. */
 int b9gw_vshard_bounds(long long n_stars, int n_vshards, int shard,
                        long long *lo, long long *hi);
 

@@ -27,13 +27,14 @@
 #define ILP_TRANS 4
 
 /* Result every thread with (threadIdx & 31) == lane stores in b9gw_dfma_peak. */
-double b9ref_dfma_lane(int lane, double a, double b, int iters) {
+double b9ref_dfma_lane(int lane, int ilp, double a, double b, int iters) {
     double x[ILP_DFMA];
-    for (int j = 0; j < ILP_DFMA; ++j) x[j] = 1.0 + 0.125 * j + lane * 0x1p-10;
+    if (ilp < 1 || ilp > ILP_DFMA) return NAN;
+    for (int j = 0; j < ilp; ++j) x[j] = 1.0 + 0.125 * j + lane * 0x1p-10;
     for (int i = 0; i < iters; ++i)
-        for (int j = 0; j < ILP_DFMA; ++j) x[j] = fma(x[j], a, b);
+        for (int j = 0; j < ilp; ++j) x[j] = fma(x[j], a, b);
     double s = x[0];
-    for (int j = 1; j < ILP_DFMA; ++j) s += x[j];
+    for (int j = 1; j < ilp; ++j) s += x[j];
     return s;
 }
 
@@ -131,19 +132,6 @@ void b9ref_lse_rows(const double *x, long long rows, long long cols, int warp_or
                                 : b9ref_lse_serial(x + r * cols, cols);
 }
 
-/* Sum in the order of ordered_sum_kernel: 1024 strided partials + pairwise tree. */
-double b9ref_ordered_sum(const double *v, long long n) {
-    double p[1024];
-    for (int t = 0; t < 1024; ++t) {
-        double s = 0.0;
-        for (long long i = t; i < n; i += 1024) s += v[i];
-        p[t] = s;
-    }
-    for (int w = 512; w > 0; w >>= 1)
-        for (int t = 0; t < w; ++t) p[t] += p[t + w];
-    return p[0];
-}
-
 double b9ref_serial_sum(const double *v, long long n) {
     double s = 0.0;
     for (long long i = 0; i < n; ++i) s += v[i];
@@ -155,9 +143,10 @@ double b9ref_serial_sum(const double *v, long long n) {
  * Every operation is rounded once, as written; -ffp-contract=off keeps it so. */
 double b9ref_gen_term(long long row, long long col, long long cols) {
     const double colsd = (double)cols;
+    const double inv_cols = 1.0 / colsd;                 /* rounded once, then multiplied */
     const double u = (double)row * 0.6180339887498949;
     const double c0 = (u - floor(u)) * colsd;
-    const double w = (double)(34 + (int)(row % 7)) / colsd;
+    const double w = (double)(34 + (int)(row % 7)) * inv_cols;
     const double b = -(c0 * w);
     const double t = fma((double)col, w, b);
     return -(t * t);

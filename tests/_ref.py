@@ -15,11 +15,10 @@ _pd = C.POINTER(_d)
 class Ref:
     def __init__(self, path):
         L = C.CDLL(str(path))
-        L.b9ref_dfma_lane.restype, L.b9ref_dfma_lane.argtypes = _d, [_i, _d, _d, _i]
+        L.b9ref_dfma_lane.restype, L.b9ref_dfma_lane.argtypes = _d, [_i, _i, _d, _d, _i]
         L.b9ref_trans_lane.restype, L.b9ref_trans_lane.argtypes = _d, [_i, _i, _i]
         L.b9ref_map.restype, L.b9ref_map.argtypes = None, [_i, _pd, _pd, _ll]
         L.b9ref_lse_rows.restype, L.b9ref_lse_rows.argtypes = None, [_pd, _ll, _ll, _i, _pd]
-        L.b9ref_ordered_sum.restype, L.b9ref_ordered_sum.argtypes = _d, [_pd, _ll]
         L.b9ref_serial_sum.restype, L.b9ref_serial_sum.argtypes = _d, [_pd, _ll]
         L.b9ref_spread_args.restype, L.b9ref_spread_args.argtypes = None, [_i, _i, _i, _i, _pd]
         L.b9ref_gen_term.restype, L.b9ref_gen_term.argtypes = _d, [_ll, _ll, _ll]
@@ -33,8 +32,8 @@ class Ref:
     def _p(a):
         return a.ctypes.data_as(_pd)
 
-    def dfma_lanes(self, a, b, iters):
-        return np.array([self.L.b9ref_dfma_lane(l, a, b, iters) for l in range(32)])
+    def dfma_lanes(self, a, b, iters, ilp=8):
+        return np.array([self.L.b9ref_dfma_lane(l, ilp, a, b, iters) for l in range(32)])
 
     TRANS = {"exp": 0, "log": 1, "exp10": 2, "log10": 3, "exp_spread": 4, "log_spread": 5}
     MAP = {"exp": 0, "log": 1, "exp10": 2, "log10": 3, "pow10": 12}
@@ -79,9 +78,10 @@ class Ref:
         self.L.b9ref_lse_rows(self._p(x), x.shape[0], x.shape[1], int(warp_order), self._p(out))
         return out
 
-    def ordered_sum(self, v):
-        v = np.ascontiguousarray(v, dtype=np.float64)
-        return self.L.b9ref_ordered_sum(self._p(v), v.size)
+    def rows_total(self, row_values, V=64):
+        """(P[V], total) of a vector of row values: the virtual-shard sum with one chain."""
+        P, t = self.vshard_total(np.asarray(row_values, dtype=np.float64)[None, :], V)
+        return P[:, 0], t[0]
 
     def serial_sum(self, v):
         v = np.ascontiguousarray(v, dtype=np.float64)

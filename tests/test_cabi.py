@@ -63,8 +63,9 @@ def test_sizes_that_would_wrap_are_rejected_before_any_allocation(built):
     from base_b200 import groundwork as gw
     L, t = gw.lib(), C.c_double()
     big = 1 << 62
-    assert L.b9gw_lse_rows(0, None, big, 4, 0, 1, None, C.byref(t), None) == gw.E_ARG
-    assert L.b9gw_lse_generated(0, big, big, 0, 1, None, C.byref(t), None) == gw.E_ARG
+    assert L.b9gw_lse_rows(0, None, big, 4, 64, 0, 1, None, None, C.byref(t), None) == gw.E_ARG
+    assert L.b9gw_lse_generated(0, big, big, 64, 0, 1, None, None, C.byref(t), None) == gw.E_ARG
+    assert L.b9gw_lse_generated(0, 8, 8, 48, 0, 1, None, None, C.byref(t), None) == gw.E_ARG
     assert L.b9gw_generate_terms(0, big, 8, None) == gw.E_ARG
     assert L.b9gw_map(0, 0, None, None, big) == gw.E_ARG
     assert L.b9gw_map(0, 7, None, None, 0) == gw.E_ARG

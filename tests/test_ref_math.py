@@ -59,14 +59,18 @@ def test_reduction_order_effect_is_far_inside_1e_10(ref):
     assert mixed_err(w, s) < 2e-14
     # ...but NOT small relative to a row value that happens to sit near zero:
     assert np.max(np.abs(s - w) / np.abs(s)) > 1e-13
-    tot_tree, tot_serial = ref.ordered_sum(s), ref.serial_sum(s)
-    assert abs(tot_tree - tot_serial) / abs(tot_serial) < 1e-13
+    (_, tot_shards), tot_serial = ref.rows_total(s), ref.serial_sum(s)
+    assert abs(tot_shards - tot_serial) / abs(tot_serial) < 1e-13
 
 
-def test_ordered_sum_small_and_ragged(ref):
-    assert ref.ordered_sum(np.empty(0)) == 0.0
+def test_rows_total_small_and_ragged(ref):
+    P, t = ref.rows_total(np.empty(0))
+    assert t == 0.0 and (P == 0.0).all()
     v = np.arange(1, 2050, dtype=np.float64)
-    assert ref.ordered_sum(v) == v.sum() == 2049 * 2050 / 2
+    for V in (4, 64, 128):
+        assert ref.rows_total(v, V)[1] == v.sum() == 2049 * 2050 / 2
+    P, t = ref.rows_total(np.array([3.0, 5.0]), 8)       # fewer rows than shards: empty shards add +0
+    assert t == 8.0 and sorted(P) == [0.0] * 6 + [3.0, 5.0]
 
 
 def test_generator_is_the_stated_arithmetic_rounded_once_per_operation(ref):
@@ -78,7 +82,7 @@ def test_generator_is_the_stated_arithmetic_rounded_once_per_operation(ref):
         for r in (0, 1, rows - 1):
             u = float(Fraction(r) * Fraction(phi))
             c0 = float(Fraction(float(Fraction(u) - math.floor(u))) * cols)
-            w = float(Fraction(34 + r % 7) / cols)
+            w = float(Fraction(34 + r % 7) * Fraction(float(Fraction(1) / cols)))
             b = -float(Fraction(c0) * Fraction(w))
             for c in (0, 1, cols // 2, cols - 1):
                 t = float(Fraction(c) * Fraction(w) + Fraction(b))        # fma: one rounding
