@@ -136,7 +136,7 @@ __global__ void map_exp_fast_path_kernel(const __grid_constant__ b9gw::ExpConsta
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (; i < n; i += stride) {
-        const double in[1] = {x[i]};
+        const double in[1] = {-x[i]};
         double out[1];
         b9gw::exp_fast_path(K, in, out);
         y[i] = out[0];

@@ -220,18 +220,21 @@ lse_staged_kernel(const __grid_constant__ ExpConstants K, const double *__restri
             // pass 2: lane l adds exp(term - m) over c = l, l+32, ... in increasing c
             double s = 0.0;
             for (int k = 0; k < iters; k += 4) {
-                double d[4], e[4];
+                double neg[4], e[4];
                 bool fast = true;
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    d[i] = __dsub_rn(buf[32 * (k + i)], m);
-                    fast &= d[i] > -708.0;                 // false for NaN as well
+                    // -708 < term - m <= 0 tested on the integer pipe: m - term is the exact
+                    // negation of term - m and never negative, so its high word grows with its
+                    // magnitude; +inf and NaN of either sign land above the bound
+                    neg[i] = __dsub_rn(m, buf[32 * (k + i)]);
+                    fast &= (unsigned)__double2hiint(neg[i]) < 0x40862000u;
                 }
                 if (__all_sync(FULL, fast)) {
-                    exp_fast_path(K, d, e);
+                    exp_fast_path(K, neg, e);
                 } else {
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) e[i] = exp(d[i]);
+                    for (int i = 0; i < 4; ++i) e[i] = exp(-neg[i]);
                 }
 #pragma unroll
                 for (int i = 0; i < 4; ++i) s = __dadd_rn(s, e[i]);
@@ -305,10 +308,21 @@ int env_int(const char *name, int lo, int hi, int dflt) {   // tuning aids, not 
     return n >= lo && n <= hi ? n : dflt;
 }
 
-// Rows a staged warp takes in sequence (amortises the ticket round trip that ends its work).
-int rows_per_warp() {
-    static int v = env_int("B9GW_LSE_ROWS_PER_WARP", 1, 64, 2);
-    return v;
+// Rows a staged warp takes in sequence.  More rows per warp amortise the ticket round trip
+// that ends a warp's work, but with fewer rows than ~8 per resident warp slot they only
+// lengthen the critical path: measured on B200 (profiles/r02_groundwork.md), 1 is best at
+// 10 000 rows and 4 at 160 000.
+int rows_per_warp(long long rows) {
+    static int forced = env_int("B9GW_LSE_ROWS_PER_WARP", 1, 64, 0);
+    if (forced) return forced;
+    static int slots = [] {
+        int dev = 0, sms = 148;
+        if (cudaGetDevice(&dev) == cudaSuccess)
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        return sms * 24;                   // 6 CTAs of 4 warps fit one SM's shared memory at 1024 columns
+    }();
+    const long long per_slot = rows / slots;
+    return per_slot >= 8 ? 4 : per_slot >= 4 ? 2 : 1;
 }
 
 template <int SRC>
@@ -318,7 +332,7 @@ cudaError_t launch_lse(cudaStream_t st, const double *x, long long rows, long lo
     if (rows == 0) {
         no_rows_kernel<<<1, 128, 0, st>>>(partials, V, total);
     } else if (cols <= B9GW_LSE_STAGED_COLS) {
-        const int cap = (int)((cols + 127) / 128 * 128), rpw = rows_per_warp();
+        const int cap = (int)((cols + 127) / 128 * 128), rpw = rows_per_warp(rows);
         const long long per_cta = (long long)STAGED_WARPS * rpw;
         const unsigned grid = (unsigned)((rows + per_cta - 1) / per_cta);
         lse_staged_kernel<SRC><<<grid, STAGED_WARPS * 32, sizeof(double) * STAGED_WARPS * cap, st>>>(

@@ -181,8 +181,8 @@ def main() -> int:
         "config": {"workload": "BLOCKED — no BASE-9 likelihood exists to run; see `blocked`",
                    "step": "undefined: there is no likelihood evaluation to call a step; --steps/--warmup "
                            "only size the timing loops of the groundwork kernels below",
-                   "l2": "n/a for the headline; lse_rows input (82 MB) is under the 126 MB L2 and is "
-                         "reported as such, lse_generated reads no input at all"},
+                   "l2": "n/a for the headline; lse rows_10000x1024 (82 MB) is under the 126 MB L2, "
+                         "rows_40000x1024 (328 MB) is not, generated_* read no input at all"},
         "blocked": status.reason if status.blocked else
         "source now staged — SURVEY.md must be redone from it before a hot path exists: " + status.reason,
         "e2e": None, "roofline": None, "cpu_baseline": None,
@@ -226,18 +226,33 @@ def main() -> int:
             launches += t["launches"]
         lat = gw.step_latency(local, warmup=50, reps=2000)
         launches += lat["launches"]
-        rows, cols = 10_000, 1_024
-        x = np.random.default_rng(1234).normal(-40.0, 12.0, size=(rows, cols))
-        s = gw.lse_rows(x, local, warmup=warmup, reps=steps)
-        g_ = gw.lse_generated(rows, cols, local, warmup=warmup, reps=steps)
-        launches += s["launches"] + g_["launches"]
+        # dependent-issue latency of the FP64 pipe: 2 chains in flight per scheduler
+        l1 = gw.dfma_peak(local, ctas_per_sm=1, ilp=1, iters=1 << 16, warmup=warmup, reps=few)
+        launches += l1["launches"]
+        cols = 1_024
+        lse = {}
+        # 10 000 rows = one proposal over a cfg2-sized cluster: latency-bound (one wave of work);
+        # 160 000 rows = 16 proposals batched in one launch, which is what north_star prescribes
+        for rows in (10_000, 160_000):
+            g_ = gw.lse_generated(rows, cols, local, warmup=warmup, reps=steps)
+            lse[f"generated_{rows}x{cols}"] = (rows, g_, False)
+            launches += g_["launches"]
+        rng = np.random.default_rng(1234)
+        for rows in (10_000, 40_000):      # 82 MB sits in the 126 MB L2; 328 MB does not
+            x = rng.normal(-40.0, 12.0, size=(rows, cols))
+            s_ = gw.lse_rows(x, local, warmup=warmup, reps=steps)
+            lse[f"rows_{rows}x{cols}"] = (rows, s_, True)
+            launches += s_["launches"]
+            del x
         vs, n = _vshard_section(gw, rank, world, local, warmup, steps)
         launches += n
     clocks = cs.summary()
 
-    def lse_line(res, reads_matrix):
+    mhz = gw.device_info(local)["sm_clock_mhz"]
+
+    def lse_line(rows, res, reads_matrix):
         sec = res["ms_per_launch"] * 1e-3
-        d = {"rows": rows, "cols": cols, "ms_per_launch": round(res["ms_per_launch"], 4),
+        d = {"ms_per_launch": round(res["ms_per_launch"], 4),
              "gterms_per_s": round(rows * cols / sec * 1e-9, 2),
              "frac_of_exp_spread_rate": round(rows * cols / sec * 1e-9 / rates["exp_spread"], 3)}
         if reads_matrix:
@@ -248,12 +263,14 @@ def main() -> int:
         "note": "reference-independent denominators and plumbing; NOT the BASE-9 hot path",
         "fp64_dfma_tflops": round(r["tflops"], 3), "dfma_ms_per_launch": round(r["ms_per_launch"], 4),
         "dfma_tflops_by_warps_per_sm": occ,
+        # 2 chains in flight per scheduler: warp-DFMAs per cycle per scheduler = 2 / latency
+        "fp64_dependent_issue_latency_clk": round(
+            2.0 / (l1["tflops"] * 1e12 / 2 / 32 / (gw.device_info(local)["sm_count"] * 4) / (mhz * 1e6)), 1),
         "fp64_gevals_per_s": rates,
         "rates_note": "exp/log/exp10/log10 are single-argument mid-range rates (contractions); "
                       "*_spread take a fresh log-uniform argument per evaluation (b9_groundwork.h)",
         "dependent_step_latency_us": {k: round(v, 2) for k, v in lat.items() if k.startswith("us_")},
-        "lse_rows": lse_line(s, True),
-        "lse_generated": lse_line(g_, False),
+        "lse": {name: lse_line(*v) for name, v in lse.items()},
         "vshard_sum": vs,
     }
     if dist is not None:
