@@ -218,6 +218,39 @@ done:
     return rc;
 }
 
+int b9gw_dev_malloc(int device, long long bytes, void **ptr_dev) {
+    if (!ptr_dev || bytes < 0) return fail(B9GW_E_ARG, "need ptr_dev and bytes>=0");
+    *ptr_dev = nullptr;
+    b9gw::DeviceGuard guard(device);
+    if (guard.rc() != B9GW_OK) return guard.rc();
+    cudaError_t e = cudaMalloc(ptr_dev, bytes > 0 ? (size_t)bytes : 1);
+    return e == cudaSuccess ? B9GW_OK : fail(B9GW_E_CUDA, "cudaMalloc", e);
+}
+
+int b9gw_dev_free(int device, void *ptr_dev) {
+    if (!ptr_dev) return B9GW_OK;
+    b9gw::DeviceGuard guard(device);
+    if (guard.rc() != B9GW_OK) return guard.rc();
+    cudaError_t e = cudaFree(ptr_dev);
+    return e == cudaSuccess ? B9GW_OK : fail(B9GW_E_CUDA, "cudaFree", e);
+}
+
+int b9gw_memcpy_h2d(int device, void *dst_dev, const void *src_host, long long bytes) {
+    if (bytes < 0 || (bytes > 0 && (!dst_dev || !src_host))) return fail(B9GW_E_ARG, "null buffer or bytes<0");
+    b9gw::DeviceGuard guard(device);
+    if (guard.rc() != B9GW_OK) return guard.rc();
+    cudaError_t e = cudaMemcpy(dst_dev, src_host, (size_t)bytes, cudaMemcpyHostToDevice);
+    return e == cudaSuccess ? B9GW_OK : fail(B9GW_E_CUDA, "cudaMemcpy H2D", e);
+}
+
+int b9gw_memcpy_d2h(int device, void *dst_host, const void *src_dev, long long bytes) {
+    if (bytes < 0 || (bytes > 0 && (!dst_host || !src_dev))) return fail(B9GW_E_ARG, "null buffer or bytes<0");
+    b9gw::DeviceGuard guard(device);
+    if (guard.rc() != B9GW_OK) return guard.rc();
+    cudaError_t e = cudaMemcpy(dst_host, src_dev, (size_t)bytes, cudaMemcpyDeviceToHost);
+    return e == cudaSuccess ? B9GW_OK : fail(B9GW_E_CUDA, "cudaMemcpy D2H", e);
+}
+
 int b9gw_dfma_peak(int device, int ctas_per_sm, int ilp, int iters, double a, double b,
                    int warmup, int reps, double *out_host, long long *n_threads,
                    float *ms_per_launch, double *tflops) {

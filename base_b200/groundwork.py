@@ -34,6 +34,10 @@ SYMBOLS = {
     "b9gw_lse_rows": (_i, [_i, _pd, _ll, _ll, _i, _i, _i, _pd, _pd, _pd, _pf]),
     "b9gw_generate_terms": (_i, [_i, _ll, _ll, _pd]),
     "b9gw_lse_generated": (_i, [_i, _ll, _ll, _i, _i, _i, _pd, _pd, _pd, _pf]),
+    "b9gw_dev_malloc": (_i, [_i, _ll, C.POINTER(_vp)]),
+    "b9gw_dev_free": (_i, [_i, _vp]),
+    "b9gw_memcpy_h2d": (_i, [_i, _vp, _vp, _ll]),
+    "b9gw_memcpy_d2h": (_i, [_i, _vp, _vp, _ll]),
     "b9gw_vshard_bounds": (_i, [_ll, _i, _i, _pll, _pll]),
     # *_dev arguments are raw device addresses (c_void_p), e.g. torch.Tensor.data_ptr()
     "b9gw_shard_partials": (_i, [_vp, _ll, _ll, _ll, _i, _i, _i, _vp, _vp]),

@@ -136,21 +136,28 @@ def _vshard_section(gw, rank: int, world: int, local: int, warmup: int, steps: i
         launches += lat["launches"]
         us = torch.tensor([lat["us_stream"], lat["us_graph"]], device=f"cuda:{local}")
         if world > 1:
-            # comparison line: the same sum stated with NCCL all-gather + V ordered adds (eager torch)
-            for _ in range(max(warmup, 5)):
-                ref = vshards.allgather_ordered_sum(P)
-            dist.barrier(); torch.cuda.synchronize()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            for _ in range(50):
-                ref = vshards.allgather_ordered_sum(P)
-            b.record()
-            torch.cuda.synchronize()
+            # comparison lines (eager torch over NCCL, launched from Python): the all-gather of the
+            # [V, chains] partials alone, and the same sum stated as all-gather + V ordered adds
+            def timed(fn, n=50):
+                for _ in range(max(warmup, 5)):
+                    r_ = fn()
+                dist.barrier(); torch.cuda.synchronize()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                for _ in range(n):
+                    r_ = fn()
+                b.record()
+                torch.cuda.synchronize()
+                return r_, a.elapsed_time(b) * 1e3 / n
+            flat = torch.empty(V * chains, dtype=torch.float64, device=P.device)
+            _, us_gather = timed(lambda: dist.all_gather_into_tensor(flat, P.view(-1)))
+            ref, us_sum = timed(lambda: vshards.allgather_ordered_sum(P))
             if not torch.equal(ref.view(torch.int64), total.view(torch.int64)):
                 raise SystemExit("peer kernel and NCCL all-gather statement disagree in bits")
-            us = torch.cat([us, torch.tensor([a.elapsed_time(b) * 1e3 / 50], device=us.device)])
+            us = torch.cat([us, torch.tensor([us_gather, us_sum], device=us.device)])
             dist.all_reduce(us, op=dist.ReduceOp.MAX)   # device-timed, max over ranks
-            out["nccl_allgather_plus_ordered_adds_us"] = round(us[2].item(), 2)
+            out["nccl_allgather_alone_us"] = round(us[2].item(), 2)
+            out["nccl_allgather_plus_ordered_adds_us"] = round(us[3].item(), 2)
             dist.barrier()                              # nobody frees a mailbox a peer still writes
         out["peer_kernel_us_stream"] = round(us[0].item(), 2)
         out["peer_kernel_us_graph"] = round(us[1].item(), 2)

@@ -181,6 +181,19 @@ int b9gw_lse_generated(int device, long long rows, long long cols, int n_vshards
                        double *partials_host, double *total_host,
                        float *ms_per_launch);
 
+/* ------------------------------------------------------- device memory */
+
+/*
+ * Plain device-memory helpers, so that a host program (the C++ chain driver)
+ * can hold the *_dev buffers of the calls below without linking the CUDA
+ * runtime itself.  Copies are synchronous and ordered after work already
+ * launched on the device's legacy default stream (cuda_stream = NULL).
+ */
+int b9gw_dev_malloc(int device, long long bytes, void **ptr_dev);
+int b9gw_dev_free(int device, void *ptr_dev);
+int b9gw_memcpy_h2d(int device, void *dst_dev, const void *src_host, long long bytes);
+int b9gw_memcpy_d2h(int device, void *dst_host, const void *src_dev, long long bytes);
+
 /* -------------------------- world-size-independent sum over virtual shards */
 
 /*

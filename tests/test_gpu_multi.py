@@ -31,3 +31,20 @@ def test_peer_comm_ranks(built, world):
     rep = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
     assert rep["bits_equal_checker"] and rep["graph_replay_ok"] and rep["missing_peer_reported"]
     print(rep)
+
+
+def test_cpp_driver_drives_the_peer_kernel_without_python(built, tmp_path):
+    """The collective is callable from a C++ host program: fork per GPU, handles through shared
+    memory, b9gw_* only.  Runs at the largest world the box allows (1 on a single-GPU box)."""
+    from base_b200 import groundwork as gw
+    exe = tmp_path / "peer_comm_c"
+    subprocess.run(["g++", "-std=c++17", "-O2", "-Wall", f"-I{ROOT / 'include'}",
+                    str(ROOT / "tests" / "multigpu" / "peer_comm_c.cpp"), "-o", str(exe),
+                    f"-L{ROOT / 'base_b200'}", "-lb9_groundwork", f"-L{ROOT / 'oracle'}", "-lb9_groundwork_ref",
+                    f"-Wl,-rpath,{ROOT / 'base_b200'}:{ROOT / 'oracle'}"], check=True)
+    world = max(w for w in (1, 2, 4, 8) if w <= gw.device_count())
+    r = subprocess.run([str(exe), str(world)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    rep = json.loads(r.stdout.strip().splitlines()[-1])
+    assert rep["world"] == world and rep["bits_equal_checker"] is True
+    print(rep)
