@@ -16,7 +16,7 @@ timeout 300 python bench.py --impl reference > $out/${tag}_bench_reference.json 
 timeout 300 python bench.py --steps 3 --warmup 3 > $out/${tag}_plain.log 2>&1 &&
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
     --log-file $out/${tag}_launches.csv python bench.py --steps 3 --warmup 3 > $out/${tag}_ncu_launches.log 2>&1 &&
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:'lse_kernel|vshard_step|shard_partials' -c 20 \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'lse_staged|lse_stream|vshard_step|shard_partials' -c 32 \
     -o $out/${tag}_lse python bench.py --steps 3 --warmup 3 > $out/${tag}_ncu_lse.log 2>&1
 echo "ncu_chain_exit=$?" > $out/${tag}_ncu_exit.txt
 tail -5 $out/${tag}_gpu_tests.log; cat $out/${tag}_bench.json; tail -3 $out/${tag}_bench.err; cat $out/${tag}_ncu_exit.txt
