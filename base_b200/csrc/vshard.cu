@@ -110,7 +110,9 @@ vshard_step_kernel(const StepArgs a) {
         // ---- pull: shards q*SLOTS .. q*SLOTS+SLOTS-1 of this chain, from the local mailbox
         const uint4 *mine = a.mail[a.rank] + (parity_base + (size_t)q * SLOTS) * (size_t)a.max_chains
                             + (size_t)chain;
-        unsigned long long t0 = 0;
+        // a comm that has already timed out is out of step with its peers for good: do not
+        // spend another timeout per launch on it
+        unsigned long long t0 = *(volatile int *)a.status ? ~0ULL : 0;
         for (;;) {
             uint4 r[SLOTS];
 #pragma unroll
@@ -123,6 +125,7 @@ vshard_step_kernel(const StepArgs a) {
                 for (int i = 0; i < SLOTS; ++i) val[i] = __hiloint2double((int)r[i].z, (int)r[i].x);
                 break;
             }
+            if (t0 == ~0ULL) { ok = false; break; }
             const unsigned long long now = globaltimer_ns();
             if (t0 == 0) t0 = now;
             else if (now - t0 > a.timeout_ns) { ok = false; break; }
@@ -259,7 +262,7 @@ int b9gw_vshard_bounds(long long n_stars, int n_vshards, int shard, long long *l
     return B9GW_OK;
 }
 
-int b9gw_shard_partials(const double *values_dev, long long chains, long long ld,
+int b9gw_shard_partials(int device, const double *values_dev, long long chains, long long ld,
                         long long n_stars_total, int n_vshards, int first_shard, int n_shards,
                         double *partial_dev, void *cuda_stream) {
     if (!vshards_ok(n_vshards) || first_shard < 0 || n_shards < 0 ||
@@ -274,8 +277,8 @@ int b9gw_shard_partials(const double *values_dev, long long chains, long long ld
     if (ld < n_local) return fail(B9GW_E_ARG, "ld is smaller than the local star count");
     if ((long long)n_shards * chains > 0 && (!partial_dev || (n_local > 0 && !values_dev)))
         return fail(B9GW_E_ARG, "null device buffer");
-    if (b9gw_device_count() == 0)
-        return fail(B9GW_E_NODEVICE, "no CUDA device visible (no CPU fallback exists)");
+    b9gw::DeviceGuard guard(device);
+    if (guard.rc() != B9GW_OK) return guard.rc();
     return launch_partials(values_dev, chains, ld, n_stars_total, n_vshards, first_shard, n_shards,
                            partial_dev, (cudaStream_t)cuda_stream);
 }

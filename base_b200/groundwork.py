@@ -40,7 +40,7 @@ SYMBOLS = {
     "b9gw_memcpy_d2h": (_i, [_i, _vp, _vp, _ll]),
     "b9gw_vshard_bounds": (_i, [_ll, _i, _i, _pll, _pll]),
     # *_dev arguments are raw device addresses (c_void_p), e.g. torch.Tensor.data_ptr()
-    "b9gw_shard_partials": (_i, [_vp, _ll, _ll, _ll, _i, _i, _i, _vp, _vp]),
+    "b9gw_shard_partials": (_i, [_i, _vp, _ll, _ll, _ll, _i, _i, _i, _vp, _vp]),
     "b9gw_comm_create": (_i, [_i, _i, _i, _i, _ll, C.POINTER(_vp), _vp]),
     "b9gw_comm_connect": (_i, [_vp, _vp]),
     "b9gw_ordered_allreduce": (_i, [_vp, _vp, _vp, _ll, _vp]),

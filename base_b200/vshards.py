@@ -122,10 +122,9 @@ class PeerComm:
         own = owned_shards(self.rank, self.world, self.n_vshards)
         chains = values.shape[0]
         out = torch.empty(len(own), chains, dtype=torch.float64, device=values.device)
-        with torch.cuda.device(self.device):
-            self._gw._ck(self._L.b9gw_shard_partials(
-                values.data_ptr(), chains, values.stride(0), n_stars_total, self.n_vshards,
-                own.start, len(own), out.data_ptr(), self._stream()))
+        self._gw._ck(self._L.b9gw_shard_partials(
+            self.device, values.data_ptr(), chains, values.stride(0), n_stars_total, self.n_vshards,
+            own.start, len(own), out.data_ptr(), self._stream()))
         return out
 
     def allreduce(self, partials: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:

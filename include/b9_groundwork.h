@@ -217,10 +217,10 @@ int b9gw_vshard_bounds(long long n_stars, int n_vshards, int shard,
  * P for the local shards.  values_dev is [chains][ld] row-major and holds this
  * rank's stars only: column 0 is star lo(first_shard).  partial_dev receives
  * [n_shards][chains].  One warp per (shard, chain); launched on `cuda_stream`
- * (a cudaStream_t; NULL = the legacy default stream) of the current device and
- * not synchronised.
+ * (a cudaStream_t of `device`; NULL = its legacy default stream) and not
+ * synchronised.
  */
-int b9gw_shard_partials(const double *values_dev, long long chains, long long ld,
+int b9gw_shard_partials(int device, const double *values_dev, long long chains, long long ld,
                         long long n_stars_total, int n_vshards, int first_shard,
                         int n_shards, double *partial_dev, void *cuda_stream);
 
@@ -256,7 +256,8 @@ int b9gw_comm_connect(b9gw_comm *comm, const void *all_handles);
  * the same sequence of calls, and each rank must own its GPU (ranks that wait
  * on one another cannot share a device).  If a peer does not arrive within the
  * comm's timeout the kernel stores NaN, raises the comm's sticky status and
- * returns; it never spins forever.
+ * returns; it never spins forever, and once the status is raised every later
+ * step on that comm fails at once (NaN) instead of waiting again.
  */
 int b9gw_ordered_allreduce(b9gw_comm *comm, const double *partial_dev,
                            double *out_dev, long long chains, void *cuda_stream);

@@ -10,9 +10,12 @@
  * What is here: closed-form host arithmetic that mirrors, operation for
  * operation, the reference-independent groundwork kernels declared in
  * include/b9_groundwork.h, so those kernels can be checked bit for bit where
- * only IEEE add/fma are involved, and to a stated ULP bound where libm is.
+ * only IEEE add/mul/div/fma are involved (the DFMA chain, the synthetic term
+ * generator, the warp-order shard partials, the virtual-shard totals), and to
+ * a stated ULP bound where libm is (exp/log/exp10/log10, the row log-sum-exp).
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may load
- * this file's library; the product path never does.
+ * this file's library; the product path never does.  oracle/b9_dump.h is the
+ * writer of the golden-vector format (tests/golden_io.py) for unblock day.
  *
  * Build: gcc -O2 -ffp-contract=off -fPIC -shared groundwork_ref.c -lm
  * (-ffp-contract=off: the only fused operations are the explicit fma() calls.)

@@ -43,7 +43,13 @@ void barrier(Shared *s, int world) {                    // sense-reversing, acro
         __atomic_store_n(&s->arrived, 0, __ATOMIC_RELAXED);
         __atomic_add_fetch(&s->generation, 1, __ATOMIC_ACQ_REL);
     } else {
-        while (__atomic_load_n(&s->generation, __ATOMIC_ACQUIRE) == gen) usleep(50);
+        for (int waited = 0; __atomic_load_n(&s->generation, __ATOMIC_ACQUIRE) == gen; waited += 50) {
+            if (waited > 30 * 1000 * 1000) {             // a rank died: do not wait for it forever
+                fprintf(stderr, "barrier: a rank never arrived; giving up\n");
+                _exit(3);
+            }
+            usleep(50);
+        }
     }
 }
 
@@ -92,19 +98,20 @@ int run_rank(int rank, int world, Shared *sh) {
     std::vector<double> got(CHAINS);
     int ok = 1;
     for (int step = 0; step < STEPS; ++step) {           // one launch pair per step, default stream
-        CHECK(b9gw_shard_partials((const double *)d_values, CHAINS, n_local, N_STARS, V, first, per,
+        CHECK(b9gw_shard_partials(rank, (const double *)d_values, CHAINS, n_local, N_STARS, V, first, per,
                                   (double *)d_partial, nullptr));
         CHECK(b9gw_ordered_allreduce(comm, (const double *)d_partial, (double *)d_out, CHAINS, nullptr));
         if (step % 50 == 49 || step == 0) {
             CHECK(b9gw_memcpy_d2h(rank, got.data(), d_out, CHAINS * 8));
             ok &= memcmp(got.data(), want.data(), CHAINS * 8) == 0;
+            if (!ok) break;                              // a wrong sum will not get better
         }
     }
     int timed_out = 0;
     unsigned long long steps = 0;
     CHECK(b9gw_comm_status(comm, &timed_out, &steps));
     ok &= !timed_out && steps == (unsigned long long)STEPS;
-    CHECK(b9gw_allreduce_latency(comm, CHAINS, 20, 400, &sh->us_stream[rank], &sh->us_graph[rank]));
+    if (ok) CHECK(b9gw_allreduce_latency(comm, CHAINS, 20, 400, &sh->us_stream[rank], &sh->us_graph[rank]));
     sh->ok[rank] = ok;
     barrier(sh, world);                                  // nobody frees a mailbox a peer still writes
     b9gw_dev_free(rank, d_values);

@@ -12,6 +12,11 @@ echo "pytest_exit=$?" >> $out/${tag}_gpu_tests.log
 timeout 300 python bench.py > $out/${tag}_bench.json 2> $out/${tag}_bench.err
 echo "bench_exit=$?" >> $out/${tag}_bench.err
 timeout 300 python bench.py --impl reference > $out/${tag}_bench_reference.json 2>&1
+# design inputs quoted in profiles/: FP64 latency vs chains in flight, LSE time vs problem size
+timeout 120 python tools/fp64_latency_probe.py > $out/${tag}_fp64_latency.log 2>&1
+for rc in "64 32" "1250 1024" "2500 1024" "5000 1024" "10000 1024" "20000 1024" "40000 1024" "160000 1024" "10000 256" "10000 512"; do
+  timeout 120 python tools/lse_probe.py $rc 20
+done > $out/${tag}_lse_sizes.log 2>&1
 # ncu only after the identical command exited 0 without it
 timeout 300 python bench.py --steps 3 --warmup 3 > $out/${tag}_plain.log 2>&1 &&
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
