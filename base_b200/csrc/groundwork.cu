@@ -37,24 +37,52 @@ using b9gw::Timer;
 // checker needs 32*ILP chains, not one per thread.  ILP 8 is the peak measurement;
 // ILP 1/2/4 at one CTA per SM (two warps per scheduler) expose the dependent-issue
 // latency: with c chains in flight per scheduler the pipe retires c DFMAs per latency.
-template <int ILP>
+// FILL 1/2 adds that many independent integer multiply-adds per DFMA: it measures whether a
+// non-FP64 instruction can issue in the shadow of a DFMA (it cannot: profiles/r02_groundwork.md).
+// FILL > 0: that many independent integer instructions per DFMA, KIND 0 = multiply-adds
+// (n <- n*n + c, one IMAD, a half-rate instruction like DFMA but on another pipe), KIND 1 =
+// add/xor pairs (n <- n + m; m <- m ^ n, full-rate ALU instructions; FILL is even).
+template <int ILP, int FILL, int KIND>
 __global__ void __launch_bounds__(B9GW_DFMA_THREADS)
 dfma_peak_kernel(double *__restrict__ out, double a, double b, int iters) {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
     double x[ILP];
+    unsigned n[ILP], q[ILP];
 #pragma unroll
-    for (int j = 0; j < ILP; ++j)
+    for (int j = 0; j < ILP; ++j) {
         x[j] = 1.0 + 0.125 * j + lane * 0x1p-10;
+        n[j] = (unsigned)t + j;
+        q[j] = (unsigned)t * 2654435761u + j;
+    }
 #pragma unroll 4
     for (int i = 0; i < iters; ++i) {
 #pragma unroll
-        for (int j = 0; j < ILP; ++j) x[j] = fma(x[j], a, b);
+        for (int j = 0; j < ILP; ++j) {
+            x[j] = fma(x[j], a, b);
+            if (KIND == 0) {
+#pragma unroll
+                for (int f = 0; f < FILL; ++f) n[j] = n[j] * n[j] + 1013904223u;   // squares do not fold
+            } else {
+#pragma unroll
+                for (int f = 0; f < FILL / 2; ++f) {
+                    n[j] += q[j];
+                    q[j] ^= n[j];
+                }
+            }
+        }
     }
     double s = x[0];
+    unsigned m = n[0] ^ q[0];
 #pragma unroll
-    for (int j = 1; j < ILP; ++j) s = __dadd_rn(s, x[j]);
-    out[t] = s;
+    for (int j = 1; j < ILP; ++j) {
+        s = __dadd_rn(s, x[j]);
+        m ^= n[j] ^ q[j];
+    }
+    // the integer work must stay live without touching the checked value: one output in 2^32
+    // would be replaced, and only when FILL > 0 and iters is large enough to reach the pattern
+    out[t] = (FILL > 0 && m == 0x9e3779b9u && iters < 0) ? -1.0 : s;
+    if (FILL > 0 && m == 0x9e3779b9u) out[t + (long long)gridDim.x * blockDim.x] = 0.0;
 }
 
 // ------------------------------------------------------- exp / log chain rate
@@ -149,7 +177,7 @@ __global__ void tick_kernel(double *out, double v) { *out = v; }
 template <class Launch>
 int run_chain_bench(int device, int ctas_per_sm, int iters, int warmup, int reps,
                     double *out_host, long long *n_threads, float *ms_per_launch,
-                    Launch launch) {
+                    Launch launch, int out_factor = 1) {
     int rc = B9GW_OK, sms = 0;
     double *d_out = nullptr;
     cudaStream_t st = nullptr;
@@ -164,7 +192,7 @@ int run_chain_bench(int device, int ctas_per_sm, int iters, int warmup, int reps
     {
         const int grid = sms * ctas_per_sm;
         nthr = (long long)grid * B9GW_DFMA_THREADS;
-        CK(cudaMalloc(&d_out, nthr * sizeof(double)));
+        CK(cudaMalloc(&d_out, nthr * out_factor * sizeof(double)));
         CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
         CK(tm.init());
         for (int i = 0; i < warmup; ++i) launch(grid, st, d_out);
@@ -251,23 +279,31 @@ int b9gw_memcpy_d2h(int device, void *dst_host, const void *src_dev, long long b
     return e == cudaSuccess ? B9GW_OK : fail(B9GW_E_CUDA, "cudaMemcpy D2H", e);
 }
 
-int b9gw_dfma_peak(int device, int ctas_per_sm, int ilp, int iters, double a, double b,
-                   int warmup, int reps, double *out_host, long long *n_threads,
+int b9gw_dfma_peak(int device, int ctas_per_sm, int ilp, int int_per_fma, int iters, double a,
+                   double b, int warmup, int reps, double *out_host, long long *n_threads,
                    float *ms_per_launch, double *tflops) {
     long long nthr = 0;
     float ms = 0.f;
     if (ilp != 1 && ilp != 2 && ilp != 4 && ilp != 8) return fail(B9GW_E_ARG, "ilp must be 1, 2, 4 or 8");
+    if ((int_per_fma != 0 && int_per_fma != 1 && int_per_fma != 2 && int_per_fma != -2 && int_per_fma != -4) ||
+        (int_per_fma != 0 && ilp != 8))
+        return fail(B9GW_E_ARG, "int_per_fma must be 0, 1, 2 (multiply-adds) or -2, -4 (ALU ops), and needs ilp = 8");
     int rc = run_chain_bench(
         device, ctas_per_sm, iters, warmup, reps, out_host, &nthr, &ms,
         [=](int grid, cudaStream_t st, double *out) {
             constexpr int T = B9GW_DFMA_THREADS;
-            switch (ilp) {
-                case 1: dfma_peak_kernel<1><<<grid, T, 0, st>>>(out, a, b, iters); break;
-                case 2: dfma_peak_kernel<2><<<grid, T, 0, st>>>(out, a, b, iters); break;
-                case 4: dfma_peak_kernel<4><<<grid, T, 0, st>>>(out, a, b, iters); break;
-                default: dfma_peak_kernel<8><<<grid, T, 0, st>>>(out, a, b, iters);
+            switch (ilp * 10 + int_per_fma) {
+                case 10: dfma_peak_kernel<1, 0, 0><<<grid, T, 0, st>>>(out, a, b, iters); break;
+                case 20: dfma_peak_kernel<2, 0, 0><<<grid, T, 0, st>>>(out, a, b, iters); break;
+                case 40: dfma_peak_kernel<4, 0, 0><<<grid, T, 0, st>>>(out, a, b, iters); break;
+                case 81: dfma_peak_kernel<8, 1, 0><<<grid, T, 0, st>>>(out, a, b, iters); break;
+                case 82: dfma_peak_kernel<8, 2, 0><<<grid, T, 0, st>>>(out, a, b, iters); break;
+                case 78: dfma_peak_kernel<8, 2, 1><<<grid, T, 0, st>>>(out, a, b, iters); break;
+                case 76: dfma_peak_kernel<8, 4, 1><<<grid, T, 0, st>>>(out, a, b, iters); break;
+                default: dfma_peak_kernel<8, 0, 0><<<grid, T, 0, st>>>(out, a, b, iters);
             }
-        });
+        },
+        int_per_fma != 0 ? 2 : 1);
     if (rc != B9GW_OK) return rc;
     if (n_threads) *n_threads = nthr;
     if (ms_per_launch) *ms_per_launch = ms;

@@ -46,7 +46,14 @@ using b9gw::exp_fast_path;
 
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int CTA_THREADS = 256;
-constexpr int STAGED_WARPS = 4;           // staged rows in flight per CTA, one warp each
+#ifndef B9GW_STAGED_WARPS
+#define B9GW_STAGED_WARPS 4
+#endif
+#ifndef B9GW_PASS2_TERMS
+#define B9GW_PASS2_TERMS 4
+#endif
+constexpr int STAGED_WARPS = B9GW_STAGED_WARPS;   // staged rows in flight per CTA, one warp each
+constexpr int PASS2_TERMS = B9GW_PASS2_TERMS;     // terms a lane exponentiates per iteration (divides 128 / 32 * k)
 constexpr int STREAM_ROWS = 8;            // rows per CTA, one warp each
 
 // ------------------------------------------------------------- term sources
@@ -222,11 +229,11 @@ lse_staged_kernel(const __grid_constant__ ExpConstants K, const double *__restri
         if (m != -INFINITY) {             // warp-uniform
             // pass 2: lane l adds exp(term - m) over c = l, l+32, ... in increasing c
             double s = 0.0;
-            for (int k = 0; k < iters; k += 4) {
-                double neg[4], e[4];
+            for (int k = 0; k < iters; k += PASS2_TERMS) {
+                double neg[PASS2_TERMS], e[PASS2_TERMS];
                 bool fast = true;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
+                for (int i = 0; i < PASS2_TERMS; ++i) {
                     // -708 < term - m <= 0 tested on the integer pipe: m - term is the exact
                     // negation of term - m and never negative, so its high word grows with its
                     // magnitude; +inf and NaN of either sign land above the bound
@@ -237,10 +244,10 @@ lse_staged_kernel(const __grid_constant__ ExpConstants K, const double *__restri
                     exp_fast_path(K, neg, e);
                 } else {
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) e[i] = exp(-neg[i]);
+                    for (int i = 0; i < PASS2_TERMS; ++i) e[i] = exp(-neg[i]);
                 }
 #pragma unroll
-                for (int i = 0; i < 4; ++i) s = __dadd_rn(s, e[i]);
+                for (int i = 0; i < PASS2_TERMS; ++i) s = __dadd_rn(s, e[i]);
             }
             r = __dadd_rn(m, log(warp_add(s)));
         }

@@ -27,7 +27,7 @@ SYMBOLS = {
     "b9gw_last_error": (C.c_char_p, []),
     "b9gw_device_count": (_i, []),
     "b9gw_device_info": (_i, [_i, _pi, _pi, _pll]),
-    "b9gw_dfma_peak": (_i, [_i, _i, _i, _i, _d, _d, _i, _i, _pd, _pll, _pf, _pd]),
+    "b9gw_dfma_peak": (_i, [_i, _i, _i, _i, _i, _d, _d, _i, _i, _pd, _pll, _pf, _pd]),
     "b9gw_transcendental_rate": (_i, [_i, _i, _i, _i, _i, _i, _pd, _pll, _pf, _pd]),
     "b9gw_step_latency": (_i, [_i, _i, _i, _pf, _pf, _pf]),
     "b9gw_map": (_i, [_i, _i, _pd, _pd, _ll]),
@@ -98,15 +98,16 @@ def device_info(device: int = 0) -> dict:
 
 
 def dfma_peak(device=0, ctas_per_sm=8, iters=1 << 16, a=1.0 - 2.0 ** -12, b=2.0 ** -12,
-              warmup=3, reps=10, want_out=False, ilp=DFMA_ILP) -> dict:
+              warmup=3, reps=10, want_out=False, ilp=DFMA_ILP, int_per_fma=0) -> dict:
     n, ms, tf = _ll(), _f(), _d()
     out = None
     if want_out:
         out = np.empty(device_info(device)["sm_count"] * ctas_per_sm * THREADS, dtype=np.float64)
-    _ck(lib().b9gw_dfma_peak(device, ctas_per_sm, ilp, iters, a, b, warmup, reps, _ptr(out),
+    _ck(lib().b9gw_dfma_peak(device, ctas_per_sm, ilp, int_per_fma, iters, a, b, warmup, reps, _ptr(out),
                              C.byref(n), C.byref(ms), C.byref(tf)))
     return {"n_threads": n.value, "ms_per_launch": ms.value, "tflops": tf.value, "out": out,
-            "iters": iters, "ctas_per_sm": ctas_per_sm, "ilp": ilp, "launches": warmup + reps}
+            "iters": iters, "ctas_per_sm": ctas_per_sm, "ilp": ilp, "int_per_fma": int_per_fma,
+            "launches": warmup + reps}
 
 
 TRANS_WHICH = {"exp": 0, "log": 1, "exp10": 2, "log10": 3, "exp_spread": 4, "log_spread": 5}

@@ -236,6 +236,12 @@ def main() -> int:
         # dependent-issue latency of the FP64 pipe: 2 chains in flight per scheduler
         l1 = gw.dfma_peak(local, ctas_per_sm=1, ilp=1, iters=1 << 16, warmup=warmup, reps=few)
         launches += l1["launches"]
+        # what other instructions cost next to FP64 work: DFMA rate with k integer companions each
+        company = {}
+        for k, name in ((1, "1_imad"), (2, "2_imad"), (-2, "2_alu"), (-4, "4_alu")):
+            c_ = gw.dfma_peak(local, ctas_per_sm=8, int_per_fma=k, iters=1 << 14, warmup=warmup, reps=few)
+            company[name] = round(c_["tflops"] / r["tflops"], 3)
+            launches += c_["launches"]
         cols = 1_024
         lse = {}
         # 10 000 rows = one proposal over a cfg2-sized cluster: latency-bound (one wave of work);
@@ -273,6 +279,9 @@ def main() -> int:
         # 2 chains in flight per scheduler: warp-DFMAs per cycle per scheduler = 2 / latency
         "fp64_dependent_issue_latency_clk": round(
             2.0 / (l1["tflops"] * 1e12 / 2 / 32 / (gw.device_info(local)["sm_count"] * 4) / (mhz * 1e6)), 1),
+        "dfma_rate_with_integer_company_per_dfma": company,
+        "issue_model": "a DFMA holds a scheduler's issue port 2 cycles, any other instruction 1: "
+                       "cycles ~ 2*n_fp64 + n_other (fits every ncu capture in profiles/r02_groundwork.md)",
         "fp64_gevals_per_s": rates,
         "rates_note": "exp/log/exp10/log10 are single-argument mid-range rates (contractions); "
                       "*_spread take a fresh log-uniform argument per evaluation (b9_groundwork.h)",

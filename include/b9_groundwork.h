@@ -77,16 +77,19 @@ int b9gw_device_info(int device, int *sm_count, int *sm_clock_mhz,
  * sum of its chains.  ilp = 8 measures the peak.  ilp = 1 with ctas_per_sm = 1
  * leaves two chains in flight per scheduler, so the time per step is half the
  * dependent-issue latency: the number a design needs to know how many
- * independent FP64 chains it must keep in flight.  Does `warmup` untimed
- * launches, then `reps` timed ones bracketed by CUDA events on the launching
- * stream.
+ * independent FP64 chains it must keep in flight.  int_per_fma (ilp 8 only)
+ * gives every DFMA independent integer instructions for company: 1 or 2 = that
+ * many multiply-adds (IMAD: half-rate, on another pipe), -2 or -4 = that many
+ * add/xor instructions (full-rate ALU).  How far the DFMA rate drops says what
+ * a non-FP64 instruction costs next to FP64 work on this part.  Does `warmup` untimed launches, then `reps` timed ones bracketed
+ * by CUDA events on the launching stream.
  *   out_host   : n_threads doubles (may be NULL) — thread t's result depends
  *                only on (t & 31); see oracle/groundwork_ref.c:b9ref_dfma_lane
  *   n_threads  : total threads launched
  *   ms_per_launch, tflops : average over `reps`; flops = 2*ilp*iters*n_threads
  */
-int b9gw_dfma_peak(int device, int ctas_per_sm, int ilp, int iters, double a, double b,
-                   int warmup, int reps, double *out_host,
+int b9gw_dfma_peak(int device, int ctas_per_sm, int ilp, int int_per_fma, int iters,
+                   double a, double b, int warmup, int reps, double *out_host,
                    long long *n_threads, float *ms_per_launch, double *tflops);
 
 /*

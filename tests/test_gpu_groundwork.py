@@ -46,6 +46,13 @@ def test_dfma_chain_bit_exact(gw, ref, iters, ctas, ilp):
     assert (bits(r["out"].reshape(-1, 32)) == bits(want)).all()
 
 
+@pytest.mark.parametrize("fill", [1, 2, -2, -4])
+def test_dfma_chain_with_integer_company_is_still_bit_exact(gw, ref, fill):
+    a, b = 1.0 - 2.0 ** -12, 2.0 ** -12
+    r = gw.dfma_peak(0, ctas_per_sm=2, iters=777, a=a, b=b, warmup=0, reps=1, want_out=True, int_per_fma=fill)
+    assert (bits(r["out"].reshape(-1, 32)) == bits(ref.dfma_lanes(a, b, 777))).all()
+
+
 def test_dfma_peak_is_within_3_percent_of_the_recorded_denominator(gw):
     r = gw.dfma_peak(0, ctas_per_sm=8, iters=1 << 16, warmup=3, reps=5)
     # 148 SMs x 64 DFMA/clk x 2 x 1.965 GHz = 37.2 TF is the arithmetic ceiling; rounds 1 and 2

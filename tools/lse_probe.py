@@ -2,6 +2,7 @@
 
     python tools/lse_probe.py [rows cols reps]
 """
+import os
 import sys
 from pathlib import Path
 
@@ -9,6 +10,9 @@ import numpy as np
 
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 from base_b200 import groundwork as gw  # noqa: E402
+
+if os.environ.get("B9GW_LIB"):            # a variant build of the library, for tuning sweeps
+    gw.LIB_PATH = Path(os.environ["B9GW_LIB"]).resolve()
 
 rows, cols, reps = (int(a) for a in (sys.argv[1:4] + ["10000", "1024", "20"][len(sys.argv) - 1:]))
 x = gw.generate_terms(rows, cols)
