@@ -19,7 +19,7 @@ for rc in "64 32" "1250 1024" "2500 1024" "5000 1024" "10000 1024" "20000 1024" 
 done > $out/${tag}_lse_sizes.log 2>&1
 # ncu only after the identical command exited 0 without it
 timeout 300 python bench.py --steps 3 --warmup 3 > $out/${tag}_plain.log 2>&1 &&
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'dfma|rate_kernel|lse_|shard|generate' -c 400 --csv \
     --log-file $out/${tag}_launches.csv python bench.py --steps 3 --warmup 3 > $out/${tag}_ncu_launches.log 2>&1 &&
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:'lse_staged|lse_stream|vshard_step|shard_partials' -c 32 \
     -o $out/${tag}_lse python bench.py --steps 3 --warmup 3 > $out/${tag}_ncu_lse.log 2>&1
