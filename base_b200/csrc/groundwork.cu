@@ -219,7 +219,7 @@ done:
 
 extern "C" {
 
-int b9gw_abi_version(void) { return 3; }
+int b9gw_abi_version(void) { return 4; }
 
 const char *b9gw_last_error(void) { return b9gw::err_buf(); }
 
@@ -251,8 +251,17 @@ int b9gw_dev_malloc(int device, long long bytes, void **ptr_dev) {
     *ptr_dev = nullptr;
     b9gw::DeviceGuard guard(device);
     if (guard.rc() != B9GW_OK) return guard.rc();
-    cudaError_t e = cudaMalloc(ptr_dev, bytes > 0 ? (size_t)bytes : 1);
-    return e == cudaSuccess ? B9GW_OK : fail(B9GW_E_CUDA, "cudaMalloc", e);
+    const size_t n = bytes > 0 ? (size_t)bytes : 1;
+    cudaError_t e = cudaMalloc(ptr_dev, n);
+    if (e != cudaSuccess) return fail(B9GW_E_CUDA, "cudaMalloc", e);
+    e = cudaMemset(*ptr_dev, 0, n);          // zero-filled, and finished before we return
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
+        cudaFree(*ptr_dev);
+        *ptr_dev = nullptr;
+        return fail(B9GW_E_CUDA, "cudaMemset", e);
+    }
+    return B9GW_OK;
 }
 
 int b9gw_dev_free(int device, void *ptr_dev) {

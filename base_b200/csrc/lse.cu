@@ -52,6 +52,13 @@ constexpr int CTA_THREADS = 256;
 #ifndef B9GW_PASS2_TERMS
 #define B9GW_PASS2_TERMS 4
 #endif
+// Without a minimum-CTAs launch bound ptxas schedules for full occupancy (32 registers a
+// thread) and un-interleaves the four exps of pass 2 into 1 + 1 + 2 dependent chains; shared
+// memory allows 6 CTAs per SM anyway.  With the bound it keeps all four chains interleaved
+// (62 registers): 304 instead of 330 us at 160 000 x 1024 (gpurun A/B, profiles/r03_*).
+#ifndef B9GW_STAGED_MIN_CTAS
+#define B9GW_STAGED_MIN_CTAS 8
+#endif
 constexpr int STAGED_WARPS = B9GW_STAGED_WARPS;   // staged rows in flight per CTA, one warp each
 constexpr int PASS2_TERMS = B9GW_PASS2_TERMS;     // terms a lane exponentiates per iteration (divides 128 / 32 * k)
 constexpr int STREAM_ROWS = 8;            // rows per CTA, one warp each
@@ -91,7 +98,7 @@ __device__ __forceinline__ double warp_add(double s) {
     return s;
 }
 
-__device__ __forceinline__ long long shard_lo(long long n, int shift, long long v) {
+__host__ __device__ __forceinline__ long long shard_lo(long long n, int shift, long long v) {
     return (long long)(((unsigned long long)v * (unsigned long long)n) >> shift);
 }
 
@@ -115,64 +122,90 @@ __device__ __forceinline__ unsigned ticket_add(unsigned *p, unsigned v) {
     return old;
 }
 
-// Called by one whole warp once the row values of rows [row0, row1) are stored — all of
-// them by this warp's lane 0, which also takes the tickets, so a ticket releases them.
-// The warp that completes a virtual shard adds that shard's row values; the warp that
-// completes the last shard adds the shards left to right.  Which warp that is does not
-// change any bit.  tickets[0..V-1] count finished rows per shard, tickets[V] finished
-// shards; each is reset by its last user, ready for the next launch on the stream.
-__device__ void finish_rows(long long row0, long long row1, long long rows, int vshift,
-                            double *row_lse, double *partials, double *total,
-                            unsigned *tickets, int lane) {
-    const int V = 1 << vshift;
-    const long long v0 = (((row0 + 1) << vshift) + rows - 1) / rows - 1;   // shard holding row0
+// One launch works on `chains` independent chains (blockIdx.y) over the stars of the local
+// virtual shards [first_shard, first_shard + n_shards) of an n_total-star job; local star s is
+// global star star0 + s.  With all V shards local the launch also produces total[chain].
+struct LseArgs {
+    const double *x;                       // SRC 0: [chains][n_local][cols]
+    double *row_lse;                       // [chains][n_local]
+    double *partials;                      // [n_shards][chains]
+    double *total;                         // [chains] or null; written only when n_shards == V
+    unsigned *tickets;                     // [chains][n_shards + 1], zero between launches
+    long long n_local, n_total, star0, chains, cols_ll;
+    double inv_cols;
+    int cols, cap, rpw, vshift, first_shard, n_shards;
+};
+
+// Called by one whole warp once the row values of local stars [s0, s1) of `chain` are
+// stored — all of them by this warp's lane 0, which also takes the tickets, so a ticket
+// releases them.  The warp that completes a virtual shard adds that shard's row values; with
+// all shards local, the warp that completes the chain's last shard adds the shards left to
+// right.  Which warp that is does not change any bit.  tickets[chain][k] counts finished
+// rows of local shard k, tickets[chain][n_shards] finished shards; each is reset by its last
+// user, ready for the next launch on the stream.
+__device__ void finish_rows(const LseArgs &a, long long chain, long long s0, long long s1, int lane) {
+    const int V = 1 << a.vshift;
+    const long long g0 = a.star0 + s0, g1 = a.star0 + s1;
+    unsigned *tk = a.tickets + chain * (a.n_shards + 1);
+    const double *rows = a.row_lse + chain * a.n_local;
     bool all_done = false;
-    for (long long v = v0; v < V; ++v) {
-        const long long lo = shard_lo(rows, vshift, v), hi = shard_lo(rows, vshift, v + 1);
-        if (lo >= row1) break;
-        if (hi <= lo) continue;                            // empty shard (rows < V)
-        const unsigned mine = (unsigned)((hi < row1 ? hi : row1) - (lo > row0 ? lo : row0));
+    for (long long v = (((g0 + 1) << a.vshift) + a.n_total - 1) / a.n_total - 1;    // shard holding g0
+         v < a.first_shard + a.n_shards; ++v) {
+        const long long lo = shard_lo(a.n_total, a.vshift, v), hi = shard_lo(a.n_total, a.vshift, v + 1);
+        if (lo >= g1) break;
+        if (hi <= lo) continue;                            // empty shard (n_total < V)
+        const unsigned mine = (unsigned)((hi < g1 ? hi : g1) - (lo > g0 ? lo : g0));
+        const int k = (int)(v - a.first_shard);
         unsigned done = 0;
-        if (lane == 0) done = ticket_add(&tickets[v], mine) + mine == (unsigned)(hi - lo);
+        if (lane == 0) done = ticket_add(&tk[k], mine) + mine == (unsigned)(hi - lo);
         if (!__shfl_sync(FULL, done, 0)) continue;
         // lane 0's acquire ordered the other warps' row values before the shuffle above; the
         // loads below bypass L1 (ld.cg), so no further fence is needed (each fence here is a
         // round trip on the kernel's serial tail, ~1.5 us apiece measured)
-        const double p = warp_ordered_sum(row_lse, lo, hi, lane);
+        const double p = warp_ordered_sum(rows, lo - a.star0, hi - a.star0, lane);
         done = 0;
         if (lane == 0) {
-            partials[v] = p;
-            tickets[v] = 0;
-            const unsigned nonempty = rows < V ? (unsigned)rows : (unsigned)V;
-            done = ticket_add(&tickets[V], 1u) + 1u == nonempty;
+            a.partials[(long long)k * a.chains + chain] = p;
+            tk[k] = 0;
+            if (a.n_shards == V && a.total) {
+                const unsigned nonempty = a.n_total < V ? (unsigned)a.n_total : (unsigned)V;
+                done = ticket_add(&tk[V], 1u) + 1u == nonempty;
+            }
         }
         all_done |= __shfl_sync(FULL, done, 0) != 0;
     }
     if (!all_done) return;
     double pk[B9GW_MAX_VSHARDS / 32];
 #pragma unroll
-    for (int k = 0; k < B9GW_MAX_VSHARDS / 32; ++k) {
-        const int u = lane + 32 * k;
-        pk[k] = 0.0;
-        if (u < V) {
-            if (shard_lo(rows, vshift, u + 1) > shard_lo(rows, vshift, u)) pk[k] = __ldcg(partials + u);
-            else partials[u] = 0.0;                        // an empty shard contributes +0
-        }
+    for (int q = 0; q < B9GW_MAX_VSHARDS / 32; ++q) {
+        const int u = lane + 32 * q;
+        pk[q] = u < V ? __ldcg(a.partials + (long long)u * a.chains + chain) : 0.0;   // empty shards hold +0
     }
     double acc = 0.0;
 #pragma unroll
-    for (int k = 0; k < B9GW_MAX_VSHARDS / 32; ++k) {
-        if (32 * k >= V) break;                            // warp-uniform
+    for (int q = 0; q < B9GW_MAX_VSHARDS / 32; ++q) {
+        if (32 * q >= V) break;                            // warp-uniform
 #pragma unroll 8
         for (int u = 0; u < 32; ++u) {                     // shuffles pipeline; only the adds are serial
-            const double pv = __shfl_sync(FULL, pk[k], u);
-            if (32 * k + u < V) acc = __dadd_rn(acc, pv);
+            const double pv = __shfl_sync(FULL, pk[q], u);
+            if (32 * q + u < V) acc = __dadd_rn(acc, pv);
         }
     }
     if (lane == 0) {
-        *total = acc;
-        tickets[V] = 0;
+        a.total[chain] = acc;
+        tk[V] = 0;
     }
+}
+
+// Empty local shards (fewer stars than shards) complete nothing: their P is +0, written here
+// by the first warp of each chain's first CTA before any ticket can be taken.
+__device__ __forceinline__ void zero_empty_shards(const LseArgs &a, long long chain, int lane) {
+    for (int k = lane; k < a.n_shards; k += 32) {
+        const long long v = a.first_shard + k;
+        if (shard_lo(a.n_total, a.vshift, v + 1) <= shard_lo(a.n_total, a.vshift, v))
+            a.partials[(long long)k * a.chains + chain] = 0.0;
+    }
+    __syncwarp();                          // ordered before lane 0's first ticket, which releases them
 }
 
 // Exact max without fmax's NaN fix-up: m is never NaN, and a NaN term compares false
@@ -186,20 +219,19 @@ __device__ __forceinline__ double max_keep(double m, double v) { return v > m ? 
 // otherwise the warp calls exp() itself.  Trip counts are warp-uniform; the padding columns
 // hold -inf, whose exp is +0 and changes no bit of the sum.
 template <int SRC>
-__global__ void __launch_bounds__(STAGED_WARPS * 32)
-lse_staged_kernel(const __grid_constant__ ExpConstants K, const double *__restrict__ x,
-                  long long rows, int n, int cap, int rpw,
-                  double inv_cols, int vshift, double *__restrict__ row_lse,
-                  double *__restrict__ partials, double *__restrict__ total,
-                  unsigned *__restrict__ tickets) {
+__global__ void __launch_bounds__(STAGED_WARPS * 32, B9GW_STAGED_MIN_CTAS)
+lse_staged_kernel(const __grid_constant__ ExpConstants K, const __grid_constant__ LseArgs a) {
     extern __shared__ double sm[];        // [STAGED_WARPS][cap]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n = a.cols, cap = a.cap;
     double *buf = sm + warp * cap + lane;
     const int iters = cap >> 5;           // multiple of 4
-    const long long row0 = ((long long)blockIdx.x * STAGED_WARPS + warp) * rpw;
-    const long long row1 = row0 + rpw < rows ? row0 + rpw : rows;
+    const long long chain = blockIdx.y;
+    const long long s0 = ((long long)blockIdx.x * STAGED_WARPS + warp) * a.rpw;
+    const long long s1 = s0 + a.rpw < a.n_local ? s0 + a.rpw : a.n_local;
+    if (blockIdx.x == 0 && warp == 0 && a.n_total < (1LL << a.vshift)) zero_empty_shards(a, chain, lane);
 
-    for (long long row = row0; row < row1; ++row) {
+    for (long long s = s0; s < s1; ++s) {
         // pass 1: fetch/generate once, park, max
         double m = -INFINITY;
         auto fetch = [&](auto src) {
@@ -220,15 +252,15 @@ lse_staged_kernel(const __grid_constant__ ExpConstants K, const double *__restri
                 }
             }
         };
-        if constexpr (SRC == 0) fetch(MatrixRow{x + row * n});
-        else fetch(GeneratedRow(row, n, inv_cols));
+        if constexpr (SRC == 0) fetch(MatrixRow{a.x + (chain * a.n_local + s) * n});
+        else fetch(GeneratedRow(chain * a.n_total + a.star0 + s, n, a.inv_cols));
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) m = max_keep(m, __shfl_xor_sync(FULL, m, o));
 
         double r = -INFINITY;             // every term is exp(-inf) = 0 (also n == 0)
         if (m != -INFINITY) {             // warp-uniform
             // pass 2: lane l adds exp(term - m) over c = l, l+32, ... in increasing c
-            double s = 0.0;
+            double acc = 0.0;
             for (int k = 0; k < iters; k += PASS2_TERMS) {
                 double neg[PASS2_TERMS], e[PASS2_TERMS];
                 bool fast = true;
@@ -247,25 +279,25 @@ lse_staged_kernel(const __grid_constant__ ExpConstants K, const double *__restri
                     for (int i = 0; i < PASS2_TERMS; ++i) e[i] = exp(-neg[i]);
                 }
 #pragma unroll
-                for (int i = 0; i < PASS2_TERMS; ++i) s = __dadd_rn(s, e[i]);
+                for (int i = 0; i < PASS2_TERMS; ++i) acc = __dadd_rn(acc, e[i]);
             }
-            r = __dadd_rn(m, log(warp_add(s)));
+            r = __dadd_rn(m, log(warp_add(acc)));
         }
-        if (lane == 0) row_lse[row] = r;
+        if (lane == 0) a.row_lse[chain * a.n_local + s] = r;
         __syncwarp();                     // the row's slice is reused by the next row
     }
-    if (row0 < row1) finish_rows(row0, row1, rows, vshift, row_lse, partials, total, tickets, lane);
+    if (s0 < s1) finish_rows(a, chain, s0, s1, lane);
 }
 
 // Longer rows: one warp per row, two passes over the source.
 template <int SRC>
 __global__ void __launch_bounds__(CTA_THREADS)
-lse_stream_kernel(const double *__restrict__ x, long long rows, long long cols, double inv_cols,
-                  int vshift, double *__restrict__ row_lse, double *__restrict__ partials,
-                  double *__restrict__ total, unsigned *__restrict__ tickets) {
-    const int lane = threadIdx.x & 31;
-    const long long row = (long long)blockIdx.x * STREAM_ROWS + (threadIdx.x >> 5);
-    if (row >= rows) return;
+lse_stream_kernel(const __grid_constant__ LseArgs a) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long chain = blockIdx.y, cols = a.cols_ll;
+    const long long s = (long long)blockIdx.x * STREAM_ROWS + warp;
+    if (blockIdx.x == 0 && warp == 0 && a.n_total < (1LL << a.vshift)) zero_empty_shards(a, chain, lane);
+    if (s >= a.n_local) return;
     auto lse = [&](auto src) -> double {
         constexpr int B = 8;
         double m = -INFINITY;
@@ -278,16 +310,16 @@ lse_stream_kernel(const double *__restrict__ x, long long rows, long long cols, 
         }
         m = warp_max(m);
         if (m == -INFINITY) return -INFINITY;
-        double s = 0.0;
+        double acc = 0.0;
 #pragma unroll 4
-        for (long long c = lane; c < cols; c += 32) s = __dadd_rn(s, exp(__dsub_rn(src(c), m)));
-        return __dadd_rn(m, log(warp_add(s)));
+        for (long long c = lane; c < cols; c += 32) acc = __dadd_rn(acc, exp(__dsub_rn(src(c), m)));
+        return __dadd_rn(m, log(warp_add(acc)));
     };
     double r;
-    if constexpr (SRC == 0) r = lse(MatrixRow{x + row * cols});
-    else r = lse(GeneratedRow(row, cols, inv_cols));
-    if (lane == 0) row_lse[row] = r;
-    finish_rows(row, row + 1, rows, vshift, row_lse, partials, total, tickets, lane);
+    if constexpr (SRC == 0) r = lse(MatrixRow{a.x + (chain * a.n_local + s) * cols});
+    else r = lse(GeneratedRow(chain * a.n_total + a.star0 + s, cols, a.inv_cols));
+    if (lane == 0) a.row_lse[chain * a.n_local + s] = r;
+    finish_rows(a, chain, s, s + 1, lane);
 }
 
 __global__ void __launch_bounds__(256)
@@ -301,9 +333,13 @@ generate_terms_kernel(double *__restrict__ x, long long rows, long long cols, do
     }
 }
 
-__global__ void no_rows_kernel(double *partials, int V, double *total) {   // the empty sum
-    for (int v = threadIdx.x; v < V; v += blockDim.x) partials[v] = 0.0;
-    if (threadIdx.x == 0) *total = 0.0;
+__global__ void no_stars_kernel(double *partials, long long n_partials, double *total, long long chains) {
+    const long long stride = (long long)gridDim.x * blockDim.x;      // the empty sum, per chain
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_partials; i += stride)
+        partials[i] = 0.0;
+    if (total)
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < chains; i += stride)
+            total[i] = 0.0;
 }
 
 inline int log2_of(int V) {
@@ -336,24 +372,58 @@ int rows_per_warp(long long rows) {
 }
 
 template <int SRC>
-cudaError_t launch_lse(cudaStream_t st, const double *x, long long rows, long long cols, int V,
-                       double *row_lse, double *partials, double *total, unsigned *tickets) {
-    const double inv_cols = cols > 0 ? 1.0 / (double)cols : 0.0;
-    if (rows == 0) {
-        no_rows_kernel<<<1, 128, 0, st>>>(partials, V, total);
-    } else if (cols <= B9GW_LSE_STAGED_COLS) {
-        const int cap = (int)((cols + 127) / 128 * 128), rpw = rows_per_warp(rows);
-        const long long per_cta = (long long)STAGED_WARPS * rpw;
-        const unsigned grid = (unsigned)((rows + per_cta - 1) / per_cta);
-        lse_staged_kernel<SRC><<<grid, STAGED_WARPS * 32, sizeof(double) * STAGED_WARPS * cap, st>>>(
-            exp_constants(), x, rows, (int)cols, cap, rpw, inv_cols, log2_of(V), row_lse, partials,
-            total, tickets);
+cudaError_t launch_lse(cudaStream_t st, const double *x, const b9gw::LseJob &j, double *row_lse,
+                       double *partials, double *total, unsigned *tickets) {
+    const int vshift = log2_of(j.V);
+    LseArgs a;
+    a.x = x;
+    a.row_lse = row_lse;
+    a.partials = partials;
+    a.total = j.n_shards == j.V ? total : nullptr;
+    a.tickets = tickets;
+    a.n_total = j.n_total;
+    a.star0 = shard_lo(j.n_total, vshift, j.first_shard);
+    a.n_local = shard_lo(j.n_total, vshift, j.first_shard + j.n_shards) - a.star0;
+    a.chains = j.chains;
+    a.inv_cols = j.cols > 0 ? 1.0 / (double)j.cols : 0.0;
+    a.cols = (int)j.cols;                  // the staged kernel's; the stream kernel reads cols_ll
+    a.cols_ll = j.cols;
+    a.cap = 0;
+    a.rpw = 1;
+    a.vshift = vshift;
+    a.first_shard = j.first_shard;
+    a.n_shards = j.n_shards;
+    if (j.chains == 0 || j.n_shards == 0) return cudaSuccess;
+    if (j.n_total == 0) {
+        no_stars_kernel<<<32, 256, 0, st>>>(partials, (long long)j.n_shards * j.chains, a.total, j.chains);
+    } else if (j.cols <= B9GW_LSE_STAGED_COLS) {
+        a.cap = (int)((j.cols + 127) / 128 * 128);
+        a.rpw = rows_per_warp(a.n_local * j.chains);
+        const long long per_cta = (long long)STAGED_WARPS * a.rpw;
+        const long long gx = a.n_local > 0 ? (a.n_local + per_cta - 1) / per_cta : 1;   // CTA 0 zeroes empty shards
+        lse_staged_kernel<SRC><<<dim3((unsigned)gx, (unsigned)j.chains), STAGED_WARPS * 32,
+                                 sizeof(double) * STAGED_WARPS * a.cap, st>>>(exp_constants(), a);
     } else {
-        const unsigned grid = (unsigned)((rows + STREAM_ROWS - 1) / STREAM_ROWS);
-        lse_stream_kernel<SRC><<<grid, CTA_THREADS, 0, st>>>(x, rows, cols, inv_cols, log2_of(V),
-                                                            row_lse, partials, total, tickets);
+        const long long gx = a.n_local > 0 ? (a.n_local + STREAM_ROWS - 1) / STREAM_ROWS : 1;
+        lse_stream_kernel<SRC><<<dim3((unsigned)gx, (unsigned)j.chains), CTA_THREADS, 0, st>>>(a);
     }
     return cudaGetLastError();
+}
+
+int check_job(const b9gw::LseJob &j) {
+    if (j.n_total < 0 || j.cols < 0 || j.chains < 0)
+        return fail(B9GW_E_ARG, "need n_stars_total>=0, cols>=0, chains>=0");
+    if (j.V < 4 || j.V > B9GW_MAX_VSHARDS || (j.V & (j.V - 1)))
+        return fail(B9GW_E_ARG, "n_vshards must be a power of two in [4,128]");
+    if (j.first_shard < 0 || j.n_shards < 0 || j.first_shard + j.n_shards > j.V)
+        return fail(B9GW_E_ARG, "bad shard range");
+    if (j.chains > B9GW_LSE_MAX_CHAINS) return fail(B9GW_E_ARG, "chains > B9GW_LSE_MAX_CHAINS");
+    // the generator takes chain * n_stars_total + star as a 32-bit row number
+    if (!b9gw::product_ok(j.chains, j.n_total) || j.chains * j.n_total > (1LL << 31) - 1)
+        return fail(B9GW_E_ARG, "chains * n_stars_total > 2^31-1");
+    if (!b9gw::product_ok(j.chains * j.n_total, j.cols) || j.cols > (1LL << 40))
+        return fail(B9GW_E_ARG, "chains*n_stars_total*cols overflows (or cols > 2^40)");
+    return B9GW_OK;
 }
 
 // Shared host body: SRC 0 uploads x_host, SRC 1 has no input at all.
@@ -367,12 +437,9 @@ int run_lse(int device, const double *x_host, long long rows, long long cols, in
     cudaStream_t st = nullptr;
     b9gw::Timer tm;
     float ms = 0.f;
-    if (rows < 0 || cols < 0 || warmup < 0 || reps < 1)
-        return fail(B9GW_E_ARG, "need rows>=0, cols>=0, warmup>=0, reps>=1");
-    if (V < 4 || V > B9GW_MAX_VSHARDS || (V & (V - 1)))
-        return fail(B9GW_E_ARG, "n_vshards must be a power of two in [4,128]");
-    if (!b9gw::product_ok(rows, cols) || rows > (1LL << 31) - 1 || cols > (1LL << 40))
-        return fail(B9GW_E_ARG, "rows*cols overflows (or rows > 2^31-1, cols > 2^40)");
+    const b9gw::LseJob job{rows, cols, 1, V, 0, V};
+    if (warmup < 0 || reps < 1) return fail(B9GW_E_ARG, "need warmup>=0, reps>=1");
+    if ((rc = check_job(job)) != B9GW_OK) return rc;
     if (SRC == 0 && rows * cols > 0 && !x_host) return fail(B9GW_E_ARG, "x_host is null");
     if (!total_host) return fail(B9GW_E_ARG, "total_host is null");
     b9gw::DeviceGuard guard(device);
@@ -395,7 +462,7 @@ int run_lse(int device, const double *x_host, long long rows, long long cols, in
                 CK(cudaStreamSynchronize(st));
                 CK(cudaEventRecord(tm.a, st));
             }
-            CK(launch_lse<SRC>(st, dx, rows, cols, V, dr, dp, dt, dtickets));
+            CK(launch_lse<SRC>(st, dx, job, dr, dp, dt, dtickets));
         }
         CK(cudaEventRecord(tm.b, st));
         CK(cudaStreamSynchronize(st));
@@ -418,6 +485,23 @@ done:
 
 }  // namespace
 
+namespace b9gw {
+
+long long lse_ticket_bytes(const LseJob &j) {
+    return (long long)sizeof(unsigned) * j.chains * (j.n_shards + 1);
+}
+
+int launch_lse_generated(cudaStream_t st, const LseJob &j, double *row_lse, double *partials,
+                         double *total, unsigned *tickets) {
+    int rc = check_job(j);
+    if (rc != B9GW_OK) return rc;
+    const cudaError_t e = launch_lse<1>(st, nullptr, j, row_lse, partials, total, tickets);
+    if (e != cudaSuccess) return fail(B9GW_E_CUDA, "lse kernel launch", e);
+    return B9GW_OK;
+}
+
+}  // namespace b9gw
+
 extern "C" {
 
 int b9gw_lse_rows(int device, const double *x_host, long long rows, long long cols, int n_vshards,
@@ -432,6 +516,28 @@ int b9gw_lse_generated(int device, long long rows, long long cols, int n_vshards
                        float *ms_per_launch) {
     return run_lse<1>(device, nullptr, rows, cols, n_vshards, warmup, reps, row_lse_host,
                       partials_host, total_host, ms_per_launch);
+}
+
+long long b9gw_lse_workspace_bytes(long long chains, int n_shards) {
+    if (chains < 0 || chains > B9GW_LSE_MAX_CHAINS || n_shards < 0 || n_shards > B9GW_MAX_VSHARDS)
+        return fail(B9GW_E_ARG, "need 0<=chains<=B9GW_LSE_MAX_CHAINS, 0<=n_shards<=B9GW_MAX_VSHARDS");
+    const long long b = b9gw::lse_ticket_bytes(b9gw::LseJob{0, 0, chains, B9GW_MAX_VSHARDS, 0, n_shards});
+    return b > 0 ? b : (long long)sizeof(unsigned);
+}
+
+int b9gw_lse_generated_shards(int device, long long n_stars_total, long long cols, long long chains,
+                              int n_vshards, int first_shard, int n_shards, double *row_lse_dev,
+                              double *partial_dev, double *total_dev, void *workspace_dev,
+                              void *cuda_stream) {
+    const b9gw::LseJob job{n_stars_total, cols, chains, n_vshards, first_shard, n_shards};
+    int rc = check_job(job);
+    if (rc != B9GW_OK) return rc;
+    if (chains > 0 && n_shards > 0 && (!row_lse_dev || !partial_dev || !workspace_dev))
+        return fail(B9GW_E_ARG, "null device buffer");
+    b9gw::DeviceGuard guard(device);
+    if (guard.rc() != B9GW_OK) return guard.rc();
+    return b9gw::launch_lse_generated((cudaStream_t)cuda_stream, job, row_lse_dev, partial_dev,
+                                      total_dev, (unsigned *)workspace_dev);
 }
 
 int b9gw_generate_terms(int device, long long rows, long long cols, double *x_host) {

@@ -460,6 +460,73 @@ done:
     return rc;
 }
 
+int b9gw_sharded_step(b9gw_comm *c, long long n_stars_total, long long cols, long long chains,
+                      int warmup, int reps, double *total_host, float *us_step,
+                      float *us_lse_alone) {
+    int rc = B9GW_OK, flag = 0;
+    double *drow = nullptr, *dp = nullptr, *dout = nullptr;
+    unsigned *dtk = nullptr;
+    cudaStream_t st = nullptr;
+    b9gw::Timer tm;
+    float ms = 0.f;
+    if (!c) return fail(B9GW_E_ARG, "comm is null");
+    if (!c->connected) return fail(B9GW_E_STATE, "comm is not connected");
+    if (chains < 1 || chains > c->max_chains || warmup < 0 || reps < 1)
+        return fail(B9GW_E_ARG, "need 1<=chains<=max_chains, warmup>=0, reps>=1");
+    if (n_stars_total < 0 || n_stars_total > MAX_STARS) return fail(B9GW_E_ARG, "bad n_stars_total");
+    b9gw::DeviceGuard guard(c->device);
+    if (guard.rc() != B9GW_OK) return guard.rc();
+    {
+        const int per = c->V / c->world, sh = log2_of(c->V);
+        const b9gw::LseJob job{n_stars_total, cols, chains, c->V, c->rank * per, per};
+        const long long n_local = shard_lo(n_stars_total, sh, job.first_shard + per) -
+                                  shard_lo(n_stars_total, sh, job.first_shard);
+        const long long tk_bytes = b9gw::lse_ticket_bytes(job);
+        CK(cudaMalloc(&drow, (size_t)(n_local * chains > 0 ? n_local * chains : 1) * sizeof(double)));
+        CK(cudaMalloc(&dp, (size_t)per * chains * sizeof(double)));
+        CK(cudaMalloc(&dout, chains * sizeof(double)));
+        CK(cudaMalloc(&dtk, tk_bytes));
+        CK(cudaMemset(dtk, 0, tk_bytes));
+        CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        CK(tm.init());
+        // with one rank every shard is local and the LSE launch could add the shards itself;
+        // the step is kept the same two kernels at every world size so the times compare
+        for (int i = 0; i < warmup + reps; ++i) {           // the LSE share alone (no peer involved)
+            if (i == warmup) {
+                CK(cudaStreamSynchronize(st));
+                CK(cudaEventRecord(tm.a, st));
+            }
+            if ((rc = b9gw::launch_lse_generated(st, job, drow, dp, nullptr, dtk)) != B9GW_OK) goto done;
+        }
+        CK(cudaEventRecord(tm.b, st));
+        CK(cudaStreamSynchronize(st));
+        CK(cudaEventElapsedTime(&ms, tm.a, tm.b));
+        if (us_lse_alone) *us_lse_alone = ms * 1e3f / reps;
+        for (int i = 0; i < warmup + reps; ++i) {           // the step: LSE share, then the cross-rank sum
+            if (i == warmup) {
+                CK(cudaStreamSynchronize(st));
+                CK(cudaEventRecord(tm.a, st));
+            }
+            if ((rc = b9gw::launch_lse_generated(st, job, drow, dp, nullptr, dtk)) != B9GW_OK) goto done;
+            if ((rc = launch_step(c, dp, dout, chains, st)) != B9GW_OK) goto done;
+        }
+        CK(cudaEventRecord(tm.b, st));
+        CK(cudaStreamSynchronize(st));
+        CK(cudaEventElapsedTime(&ms, tm.a, tm.b));
+        if (us_step) *us_step = ms * 1e3f / reps;
+        if (total_host) CK(cudaMemcpy(total_host, dout, chains * sizeof(double), cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(&flag, c->status, sizeof flag, cudaMemcpyDeviceToHost));
+        if (flag) rc = fail(B9GW_E_TIMEOUT, "a peer did not arrive within the comm's timeout");
+    }
+done:
+    if (st) cudaStreamDestroy(st);
+    if (drow) cudaFree(drow);
+    if (dp) cudaFree(dp);
+    if (dout) cudaFree(dout);
+    if (dtk) cudaFree(dtk);
+    return rc;
+}
+
 int b9gw_comm_destroy(b9gw_comm *c) {
     if (!c) return B9GW_OK;
     b9gw::DeviceGuard guard(c->device);

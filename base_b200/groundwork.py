@@ -13,9 +13,10 @@ from pathlib import Path
 import numpy as np
 
 LIB_PATH = Path(__file__).resolve().parent / "libb9_groundwork.so"
-ABI_VERSION = 3
+ABI_VERSION = 4
 DFMA_ILP, TRANS_ILP, THREADS = 8, 4, 256
 LSE_STAGED_COLS, MAX_WORLD, MAX_VSHARDS, IPC_HANDLE_BYTES = 1024, 16, 128, 64
+LSE_MAX_CHAINS = 65535
 E_NODEVICE, E_CUDA, E_ARG, E_TIMEOUT, E_STATE = -1, -2, -3, -4, -5
 
 # every symbol include/b9_groundwork.h declares: name -> (restype, argtypes)
@@ -34,6 +35,8 @@ SYMBOLS = {
     "b9gw_lse_rows": (_i, [_i, _pd, _ll, _ll, _i, _i, _i, _pd, _pd, _pd, _pf]),
     "b9gw_generate_terms": (_i, [_i, _ll, _ll, _pd]),
     "b9gw_lse_generated": (_i, [_i, _ll, _ll, _i, _i, _i, _pd, _pd, _pd, _pf]),
+    "b9gw_lse_workspace_bytes": (_ll, [_ll, _i]),
+    "b9gw_lse_generated_shards": (_i, [_i, _ll, _ll, _ll, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "b9gw_dev_malloc": (_i, [_i, _ll, C.POINTER(_vp)]),
     "b9gw_dev_free": (_i, [_i, _vp]),
     "b9gw_memcpy_h2d": (_i, [_i, _vp, _vp, _ll]),
@@ -47,6 +50,7 @@ SYMBOLS = {
     "b9gw_comm_set_timeout_ms": (_i, [_vp, _i]),
     "b9gw_comm_status": (_i, [_vp, _pi, C.POINTER(_ull)]),
     "b9gw_allreduce_latency": (_i, [_vp, _ll, _i, _i, _pf, _pf]),
+    "b9gw_sharded_step": (_i, [_vp, _ll, _ll, _ll, _i, _i, _pd, _pf, _pf]),
     "b9gw_comm_destroy": (_i, [_vp]),
     "b9gw_vshard_total": (_i, [_i, _pd, _ll, _ll, _i, _pd, _pd]),
 }
@@ -169,6 +173,55 @@ def lse_generated(rows: int, cols: int, device=0, warmup=0, reps=1, n_vshards=64
                                  _ptr(partials), C.byref(total), C.byref(ms)))
     return {"row_lse": row_lse, "partials": partials, "total": total.value,
             "ms_per_launch": ms.value, "launches": warmup + reps}
+
+
+class DeviceBuffer:
+    """b9gw_dev_malloc'd (zero-filled) device memory, for callers that hold no CUDA runtime."""
+
+    def __init__(self, nbytes: int, device=0):
+        self.device, self.nbytes, self.ptr = device, nbytes, _vp()
+        _ck(lib().b9gw_dev_malloc(device, nbytes, C.byref(self.ptr)))
+
+    def to_host(self, dtype, count: int) -> np.ndarray:
+        out = np.empty(count, dtype=dtype)
+        if out.nbytes:
+            _ck(lib().b9gw_memcpy_d2h(self.device, out.ctypes.data_as(_vp), self.ptr, out.nbytes))
+        return out
+
+    def free(self) -> None:
+        if self.ptr:
+            lib().b9gw_dev_free(self.device, self.ptr)
+            self.ptr = _vp()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.free()
+
+
+def lse_generated_shards(n_stars_total: int, cols: int, chains: int, n_vshards: int,
+                         first_shard: int, n_shards: int, device=0, launches=1) -> dict:
+    """One rank's share of a star-sharded job (b9gw_lse_generated_shards), through device
+    buffers of the library's own; `launches` > 1 re-runs it on the same workspace."""
+    L = lib()
+    lo = first_shard * n_stars_total // n_vshards
+    hi = (first_shard + n_shards) * n_stars_total // n_vshards
+    n_local = hi - lo
+    ws = L.b9gw_lse_workspace_bytes(chains, n_shards)
+    if ws < 0:
+        _ck(int(ws))
+    with DeviceBuffer(8 * chains * n_local, device) as rows, \
+            DeviceBuffer(8 * n_shards * chains, device) as part, \
+            DeviceBuffer(8 * chains, device) as tot, DeviceBuffer(ws, device) as work:
+        for _ in range(launches):
+            _ck(L.b9gw_lse_generated_shards(device, n_stars_total, cols, chains, n_vshards, first_shard,
+                                            n_shards, rows.ptr, part.ptr, tot.ptr, work.ptr, None))
+        out = {"row_lse": rows.to_host(np.float64, chains * n_local).reshape(chains, n_local),
+               "partials": part.to_host(np.float64, n_shards * chains).reshape(n_shards, chains),
+               "total": tot.to_host(np.float64, chains) if n_shards == n_vshards else None,
+               "workspace": work.to_host(np.uint32, ws // 4), "launches": launches}
+    return out
 
 
 def vshard_bounds(n_stars: int, n_vshards: int, shard: int) -> tuple[int, int]:

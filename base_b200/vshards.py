@@ -146,6 +146,19 @@ class PeerComm:
         return {"us_stream": a.value, "us_graph": b.value,
                 "launches": warmup + reps + 8 * (1 + (reps + 7) // 8)}
 
+    def sharded_step(self, n_stars_total: int, cols: int, chains: int, warmup: int = 3,
+                     reps: int = 20) -> dict:
+        """b9gw_sharded_step: this rank's share of the star-sharded log-sum-exp job, then the
+        cross-rank sum; total has the same bits on every rank and at every world size."""
+        import numpy as np
+        total = np.empty(chains, dtype=np.float64)
+        a, b = C.c_float(), C.c_float()
+        self._gw._ck(self._L.b9gw_sharded_step(self._h, n_stars_total, cols, chains, warmup, reps,
+                                               total.ctypes.data_as(C.POINTER(C.c_double)),
+                                               C.byref(a), C.byref(b)))
+        return {"total": total, "us_step": a.value, "us_lse_alone": b.value,
+                "launches": 3 * (warmup + reps)}
+
     def status(self) -> dict:
         """Synchronises; raises GroundworkError(E_TIMEOUT) if any step gave up waiting."""
         flag, steps = C.c_int(), C.c_ulonglong()

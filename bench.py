@@ -16,7 +16,9 @@ MEASURED_PEAKS.json), FP64 exp/log/exp10/log10 rates, the host round trip of one
 dependent step, a fixed-order row log-sum-exp fed from memory and from registers,
 and the world-size-independent cross-rank sum of 1024 per-chain scalars as one
 peer-memory kernel behind the C-ABI (its bits are asserted equal to the 1-rank
-sum on every rank, at every N).  There is no "step": K and W only size the timing
+sum on every rank, at every N), and a star-sharded step that puts the two together
+(each rank's share of a fixed synthetic log-sum-exp job, then the cross-rank sum;
+same bits at every N, asserted).  There is no "step": K and W only size the timing
 loops (CUDA events on the launching stream, W warm-up launches first).
 `gpu_launches` counts those groundwork kernels and nothing else.
 
@@ -162,6 +164,39 @@ def _vshard_section(gw, rank: int, world: int, local: int, warmup: int, steps: i
         out["peer_kernel_us_stream"] = round(us[0].item(), 2)
         out["peer_kernel_us_graph"] = round(us[1].item(), 2)
         comm.status()
+        out["sharded_step"], n = _sharded_step(gw, comm, rank, world, local, warmup, steps)
+        launches += n
+    return out, launches
+
+
+def _sharded_step(gw, comm, rank: int, world: int, local: int, warmup: int, steps: int) -> tuple[dict, int]:
+    """Star sharding with real work per rank (still NOT a likelihood: the synthetic generator).
+    A fixed job — 10 000 stars x 1024 terms x `chains` chains — is cut into the 64 virtual shards;
+    each rank runs the fixed-order log-sum-exp of its own 64/W shards and then the cross-rank sum:
+    two launches per step.  Strong scaling: the job does not grow with W.  The total's bits are
+    asserted equal, on every rank, to those the rank gets alone from all 64 shards."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    n_stars, cols, V = 10_000, 1_024, comm.n_vshards
+    out, launches = {"n_stars": n_stars, "cols": cols, "scaling": "strong", "launches_per_step": 2}, 0
+    for chains in (16, 128):
+        r = comm.sharded_step(n_stars, cols, chains, warmup=max(warmup, 3), reps=steps)
+        launches += r["launches"]
+        alone = gw.lse_generated_shards(n_stars, cols, chains, V, 0, V, local)["total"]
+        launches += 1
+        if not (r["total"].view(np.int64) == alone.view(np.int64)).all():
+            raise SystemExit(f"rank {rank}: the {world}-rank sharded step differs in bits from the 1-rank job")
+        us = torch.tensor([r["us_step"], r["us_lse_alone"]], device=f"cuda:{local}")
+        if world > 1:
+            dist.all_reduce(us, op=dist.ReduceOp.MAX)   # device-timed, max over ranks
+            dist.barrier()
+        sec = us[0].item() * 1e-6
+        out[f"chains_{chains}"] = {
+            "us_step": round(us[0].item(), 2), "us_lse_share_alone": round(us[1].item(), 2),
+            "gterms_per_s_whole_job": round(n_stars * cols * chains / sec * 1e-9, 1),
+            "bits_equal_world_1": True}
     return out, launches
 
 

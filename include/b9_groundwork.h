@@ -1,5 +1,5 @@
 /*
- * b9_groundwork.h — C-ABI of libb9_groundwork.so  (ABI version 3)
+ * b9_groundwork.h — C-ABI of libb9_groundwork.so  (ABI version 4)
  *
  * STATUS: the BASE-9 hot path is BLOCKED.  /root/reference is a
  * 4-line relocation notice (/root/reference/README.md:1-4); the base-cpp source
@@ -50,6 +50,7 @@ extern "C" {
 #define B9GW_TRANS_ILP     4    /* independent exp/log chains per thread */
 
 #define B9GW_LSE_STAGED_COLS 1024 /* rows up to this length are staged on chip */
+#define B9GW_LSE_MAX_CHAINS 65535 /* chains one b9gw_lse_generated_shards launch takes */
 
 #define B9GW_MAX_WORLD        16  /* ranks in one comm (one NVSwitch domain) */
 #define B9GW_MAX_VSHARDS      128 /* virtual shards; must be one of 4,8,16,32,64,128 */
@@ -184,6 +185,30 @@ int b9gw_lse_generated(int device, long long rows, long long cols, int n_vshards
                        double *partials_host, double *total_host,
                        float *ms_per_launch);
 
+/*
+ * One rank's share of a star-sharded job, on the device: the stars of virtual
+ * shards [first_shard, first_shard + n_shards) of an n_stars_total-star job (cut
+ * as under "world-size-independent sum" below), for `chains` independent chains
+ * in ONE launch (grid.y = chains).  The terms of (chain, star) are row
+ * chain * n_stars_total + star of the generator above, so the work a rank does
+ * depends on which stars it owns and on nothing else.  Writes
+ *   row_lse_dev  [chains][n_local]  n_local = stars in the local shards
+ *   partial_dev  [n_shards][chains] P[v][chain] — the input of b9gw_ordered_allreduce
+ *   total_dev    [chains]           only when every shard is local (n_shards ==
+ *                                   n_vshards); may be NULL, is untouched otherwise
+ * workspace_dev is b9gw_lse_workspace_bytes(chains, n_shards) bytes, zero before
+ * the first launch (b9gw_dev_malloc zero-fills); every launch leaves it zero
+ * again, and launches that share a workspace must be ordered on one stream.
+ * Launched on `cuda_stream` (NULL = the legacy default stream), not
+ * synchronised, capturable.  chains <= B9GW_LSE_MAX_CHAINS and
+ * chains * n_stars_total < 2^31.
+ */
+long long b9gw_lse_workspace_bytes(long long chains, int n_shards);
+int b9gw_lse_generated_shards(int device, long long n_stars_total, long long cols,
+                              long long chains, int n_vshards, int first_shard,
+                              int n_shards, double *row_lse_dev, double *partial_dev,
+                              double *total_dev, void *workspace_dev, void *cuda_stream);
+
 /* ------------------------------------------------------- device memory */
 
 /*
@@ -191,6 +216,7 @@ int b9gw_lse_generated(int device, long long rows, long long cols, int n_vshards
  * can hold the *_dev buffers of the calls below without linking the CUDA
  * runtime itself.  Copies are synchronous and ordered after work already
  * launched on the device's legacy default stream (cuda_stream = NULL).
+ * b9gw_dev_malloc returns zero-filled memory.
  */
 int b9gw_dev_malloc(int device, long long bytes, void **ptr_dev);
 int b9gw_dev_free(int device, void *ptr_dev);
@@ -283,6 +309,21 @@ int b9gw_comm_status(b9gw_comm *comm, int *timed_out, unsigned long long *steps)
  */
 int b9gw_allreduce_latency(b9gw_comm *comm, long long chains, int warmup,
                            int reps, float *us_stream, float *us_graph);
+
+/*
+ * A star-sharded step, end to end and timed: b9gw_lse_generated_shards over this
+ * rank's V/world shards of an (n_stars_total x cols)-term, `chains`-chain job,
+ * then b9gw_ordered_allreduce of the [V/world][chains] partials it wrote — two
+ * launches per step, back to back on one private stream, no host work between
+ * them.  total_host (may be NULL) receives total[chains] of the last step: the
+ * same bits on every rank AND at every world size, because no W enters the
+ * definition of either kernel's result.  us_lse_alone: the first launch alone
+ * (`reps` after `warmup`); us_step: both.  CUDA events on that stream; every rank
+ * must call with the same arguments.  Same limits as b9gw_lse_generated_shards.
+ */
+int b9gw_sharded_step(b9gw_comm *comm, long long n_stars_total, long long cols,
+                      long long chains, int warmup, int reps, double *total_host,
+                      float *us_step, float *us_lse_alone);
 
 /* Unmaps the peers and frees the mailbox.  The caller must make sure (barrier)
  * that no peer is still inside a step. */

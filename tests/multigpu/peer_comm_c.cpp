@@ -34,7 +34,7 @@ struct Shared {
     char handles[B9GW_MAX_WORLD][B9GW_IPC_HANDLE_BYTES];
     int arrived, generation;
     int ok[B9GW_MAX_WORLD];
-    float us_stream[B9GW_MAX_WORLD], us_graph[B9GW_MAX_WORLD];
+    float us_stream[B9GW_MAX_WORLD], us_graph[B9GW_MAX_WORLD], us_sharded[B9GW_MAX_WORLD];
 };
 
 void barrier(Shared *s, int world) {                    // sense-reversing, across processes
@@ -112,6 +112,27 @@ int run_rank(int rank, int world, Shared *sh) {
     CHECK(b9gw_comm_status(comm, &timed_out, &steps));
     ok &= !timed_out && steps == (unsigned long long)STEPS;
     if (ok) CHECK(b9gw_allreduce_latency(comm, CHAINS, 20, 400, &sh->us_stream[rank], &sh->us_graph[rank]));
+    if (ok) {
+        // a star-sharded step end to end (this rank's shards' log-sum-exp, then the cross-rank sum)
+        // against the same job done by this rank alone from all V shards in one launch
+        const long long sn = 3001, sc = 160, sch = 9;
+        std::vector<double> stepped(sch), alone(sch);
+        float us_lse = 0;
+        CHECK(b9gw_sharded_step(comm, sn, sc, sch, 2, 10, stepped.data(), &sh->us_sharded[rank], &us_lse));
+        void *d_rows, *d_p, *d_t, *d_ws;
+        CHECK(b9gw_dev_malloc(rank, sch * sn * 8, &d_rows));
+        CHECK(b9gw_dev_malloc(rank, sch * V * 8, &d_p));
+        CHECK(b9gw_dev_malloc(rank, sch * 8, &d_t));
+        CHECK(b9gw_dev_malloc(rank, b9gw_lse_workspace_bytes(sch, V), &d_ws));
+        CHECK(b9gw_lse_generated_shards(rank, sn, sc, sch, V, 0, V, (double *)d_rows, (double *)d_p,
+                                        (double *)d_t, d_ws, nullptr));
+        CHECK(b9gw_memcpy_d2h(rank, alone.data(), d_t, sch * 8));
+        ok &= memcmp(stepped.data(), alone.data(), sch * 8) == 0;
+        b9gw_dev_free(rank, d_rows);
+        b9gw_dev_free(rank, d_p);
+        b9gw_dev_free(rank, d_t);
+        b9gw_dev_free(rank, d_ws);
+    }
     sh->ok[rank] = ok;
     barrier(sh, world);                                  // nobody frees a mailbox a peer still writes
     b9gw_dev_free(rank, d_values);
@@ -144,14 +165,15 @@ int main(int argc, char **argv) {
         waitpid(p, &st, 0);
         bad |= !WIFEXITED(st) || WEXITSTATUS(st) != 0;
     }
-    float us_s = 0, us_g = 0;
+    float us_s = 0, us_g = 0, us_sh = 0;
     for (int r = 0; r < world; ++r) {
         bad |= !sh->ok[r];
         us_s = sh->us_stream[r] > us_s ? sh->us_stream[r] : us_s;
         us_g = sh->us_graph[r] > us_g ? sh->us_graph[r] : us_g;
+        us_sh = sh->us_sharded[r] > us_sh ? sh->us_sharded[r] : us_sh;
     }
     printf("{\"world\": %d, \"bits_equal_checker\": %s, \"steps\": %d, \"us_stream_max\": %.2f, "
-           "\"us_graph_max\": %.2f, \"driver\": \"C++ (no Python, no NCCL)\"}\n",
-           world, bad ? "false" : "true", STEPS, us_s, us_g);
+           "\"us_graph_max\": %.2f, \"sharded_step_us_max\": %.2f, \"driver\": \"C++ (no Python, no NCCL)\"}\n",
+           world, bad ? "false" : "true", STEPS, us_s, us_g, us_sh);
     return bad;
 }

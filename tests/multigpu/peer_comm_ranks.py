@@ -8,6 +8,8 @@ device (B200_PROFILING.md).  Checks, on every rank:
   1. the N-rank total has the bits of the checker's world-independent total;
   2. 300 back-to-back steps with changing data stay correct (mailbox parity, step counter);
   3. a CUDA-graph replay of the step stays correct;
+  3b. a star-sharded step (log-sum-exp of the rank's own shards, then the cross-rank sum) has
+     the bits of the same job run by one rank alone;
   4. a peer that skips a step costs the others one timeout, NaN outputs and a sticky status —
      not a hang.
 Prints one JSON line per rank-0 result.
@@ -77,6 +79,17 @@ def main():
             torch.cuda.synchronize()
             assert (bits(out) == want.view(np.int64)).all()
         report["graph_replay_ok"] = True
+        # 3b. a star-sharded step end to end: every rank computes ITS shards' log-sum-exp rows and
+        # partials on chip, then the cross-rank sum; the total must have the bits this rank gets
+        # alone, from all 64 shards in one launch (a 1-rank job on its own GPU)
+        sn, sc, sch = 3_001, 160, 9
+        step = comm.sharded_step(sn, sc, sch, warmup=2, reps=10)
+        alone = gw.lse_generated_shards(sn, sc, sch, V, 0, V, local)["total"]
+        assert (step["total"].view(np.int64) == alone.view(np.int64)).all(), f"rank {rank}: sharded step"
+        flat = gw.lse_generated(sch * sn, sc, local)["row_lse"].reshape(sch, sn)
+        assert (ref.vshard_total(flat, V)[1].view(np.int64) == alone.view(np.int64)).all()
+        report["sharded_step_bits_equal_world_1"] = True
+        report["sharded_step_us"] = round(step["us_step"], 2)
         lat = comm.latency(chains, warmup=20, reps=400)
         report["us_stream"], report["us_graph"] = round(lat["us_stream"], 2), round(lat["us_graph"], 2)
         dist.barrier()

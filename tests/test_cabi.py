@@ -88,3 +88,17 @@ def test_product_package_never_touches_the_checker():
         if py.name == "build.py":
             continue  # building the checker is not using it
         assert "groundwork_ref" not in text and "tests._ref" not in text and "from tests" not in text, py
+
+
+@pytest.mark.parametrize("kernel", ["lse_staged_kernelILi0", "lse_staged_kernelILi1"])
+def test_pass2_exp_chains_stay_interleaved_in_the_sass(built, kernel):
+    """The four exps a lane evaluates per pass-2 iteration must be interleaved in the SASS (one
+    dependent DFMA chain per warp cannot feed the FP64 pipe); ptxas once serialised them after an
+    unrelated change, costing 5-9 % (profiles/r03_groundwork.md).  No DFMA may be followed by more
+    than one DFMA writing the same register, and all four chains' Horner steps must be present."""
+    import sys
+    sys.path.insert(0, str(ROOT / "tools"))
+    from sass_interleave import fast_path_runs
+    runs = fast_path_runs(built.CUDA_LIB, kernel)
+    assert sum(n for _, n in runs) == 4 * 14, runs          # 14 DFMAs per exp (rounding fma .. last Horner step)
+    assert max(n for _, n in runs) <= 2, runs

@@ -279,6 +279,66 @@ def test_peer_comm_world_1_through_device_pointers_and_a_cuda_graph(gw, ref):
         assert 0.5 < lat["us_stream"] < 200.0 and 0.5 < lat["us_graph"] < 200.0
 
 
+@pytest.mark.parametrize("n_total,cols,chains,V", [
+    (1003, 96, 5, 64),        # ragged shards, padded columns
+    (10_000, 1024, 3, 64),    # cfg2-sized, full staged rows
+    (37, 50, 4, 64),          # fewer stars than shards: empty shards, ranks with no star at all
+    (700, 1500, 2, 16),       # rows longer than the staged limit (stream kernel)
+    (129, 7, 1, 128),
+])
+def test_sharded_lse_has_the_same_bits_at_every_world_size(gw, ref, n_total, cols, chains, V):
+    """b9gw_lse_generated_shards: W emulated ranks, one after the other on this GPU, each over its
+    own V/W shards.  Row values are those of the one-launch kernel over all chains*n_total rows
+    (bit-exact: same device code), the P[v][chain] they produce are the checker's over those row
+    values (bit-exact: adds only), and neither depends on W."""
+    flat = gw.lse_generated(chains * n_total, cols, 0)["row_lse"].reshape(chains, n_total)
+    wantP, want_total = ref.vshard_total(flat, V)
+    for W in (1, 2, 4, 8):
+        if V % W:
+            continue
+        per = V // W
+        P = np.empty((V, chains))
+        for r in range(W):
+            out = gw.lse_generated_shards(n_total, cols, chains, V, r * per, per, 0, launches=2)
+            lo, hi = ref.shard_lo(n_total, V, r * per), ref.shard_lo(n_total, V, (r + 1) * per)
+            assert (bits(out["row_lse"]) == bits(flat[:, lo:hi])).all(), (W, r)
+            assert not out["workspace"].any(), "tickets must be zero again after a launch"
+            P[r * per:(r + 1) * per] = out["partials"]
+            if W == 1:
+                assert (bits(out["total"]) == bits(want_total)).all()
+        assert (bits(P) == bits(wantP)).all(), W
+        assert (bits(gw.vshard_total(flat, V)["total"]) == bits(want_total)).all()
+
+
+def test_sharded_lse_rejects_bad_jobs(gw):
+    for args in [(10, 8, 1, 64, 60, 8), (10, 8, 70_000, 64, 0, 64), (1 << 24, 8, 256, 128, 0, 1),
+                 (10, 8, 1, 48, 0, 8)]:
+        with pytest.raises(gw.GroundworkError) as e:
+            gw.lse_generated_shards(*args, 0)
+        assert e.value.code == gw.E_ARG
+
+
+def test_sharded_lse_no_stars_and_no_chains(gw):
+    out = gw.lse_generated_shards(0, 16, 3, 64, 0, 64, 0)
+    assert (bits(out["partials"]) == 0).all() and (bits(out["total"]) == 0).all()
+    out = gw.lse_generated_shards(100, 16, 0, 64, 0, 64, 0)
+    assert out["partials"].size == 0
+
+
+def test_sharded_step_world_1(gw, ref):
+    """b9gw_sharded_step on one rank: LSE share + cross-rank sum, total checked against the
+    checker's sum over the one-launch kernel's row values."""
+    from base_b200 import vshards
+    n_total, cols, chains, V = 2_000, 256, 7, 64
+    flat = gw.lse_generated(chains * n_total, cols, 0)["row_lse"].reshape(chains, n_total)
+    _, want = ref.vshard_total(flat, V)
+    with vshards.PeerComm(0, 0, 1, V, max_chains=16) as comm:
+        r = comm.sharded_step(n_total, cols, chains, warmup=2, reps=5)
+        assert (bits(r["total"]) == bits(want)).all()
+        assert 0 < r["us_lse_alone"] <= r["us_step"] * 1.5
+        assert comm.status()["steps"] == 7
+
+
 def test_smoke_entry_point(gw):
     import __graft_entry__ as g
     g.smoke()
