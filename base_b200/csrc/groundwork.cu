@@ -219,7 +219,7 @@ done:
 
 extern "C" {
 
-int b9gw_abi_version(void) { return 4; }
+int b9gw_abi_version(void) { return 5; }
 
 const char *b9gw_last_error(void) { return b9gw::err_buf(); }
 

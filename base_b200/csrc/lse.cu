@@ -43,6 +43,7 @@ using b9gw::fail;
 using b9gw::ExpConstants;
 using b9gw::exp_constants;
 using b9gw::exp_fast_path;
+using b9gw::PeerArgs;
 
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int CTA_THREADS = 256;
@@ -136,18 +137,88 @@ struct LseArgs {
     int cols, cap, rpw, vshift, first_shard, n_shards;
 };
 
+// Shards 32q + lane, q = 0.., held one per lane in pk[q] (empty shards: +0), added strictly left
+// to right starting from +0.  The shuffles pipeline; only the adds are serial.
+__device__ __forceinline__ double add_shards_in_order(const double (&pk)[B9GW_MAX_VSHARDS / 32], int V) {
+    double acc = 0.0;
+#pragma unroll
+    for (int q = 0; q < B9GW_MAX_VSHARDS / 32; ++q) {
+        if (32 * q >= V) break;                            // warp-uniform
+#pragma unroll 8
+        for (int u = 0; u < 32; ++u) {
+            const double pv = __shfl_sync(FULL, pk[q], u);
+            if (32 * q + u < V) acc = __dadd_rn(acc, pv);
+        }
+    }
+    return acc;
+}
+
+// PEER: the cross-rank half of a fused step, run by the one warp per chain that knows the
+// chain's local shards are all pushed.  Polls this rank's own mailbox until the chain's V
+// packets show `step` (empty shards are known to hold +0 and are not waited for), adds them
+// left to right, stores total[chain] and moves the chain's step counter.  A peer that never
+// arrives costs the comm's timeout: NaN, sticky status — as in vshard.cu.
+__device__ void pull_and_total(const LseArgs &a, const PeerArgs &pa, long long chain, unsigned step,
+                               unsigned *tk, int lane) {
+    const int V = 1 << a.vshift;
+    const uint4 *mine = pa.mail[pa.rank] + (size_t)(step & 1u) * V * (size_t)pa.max_chains + (size_t)chain;
+    double pk[B9GW_MAX_VSHARDS / 32];
+    unsigned need = 0;
+#pragma unroll
+    for (int q = 0; q < B9GW_MAX_VSHARDS / 32; ++q) {
+        const int u = lane + 32 * q;
+        pk[q] = 0.0;
+        if (u < V && shard_lo(a.n_total, a.vshift, u + 1) > shard_lo(a.n_total, a.vshift, u)) need |= 1u << q;
+    }
+    bool ok = true;
+    unsigned long long t0 = *(volatile int *)pa.status ? ~0ULL : 0;   // a comm that timed out stays out of step
+    while (need) {
+        uint4 r[B9GW_MAX_VSHARDS / 32];
+#pragma unroll
+        for (int q = 0; q < B9GW_MAX_VSHARDS / 32; ++q)
+            if (need >> q & 1u) r[q] = b9gw::ld_packet(mine + (size_t)(lane + 32 * q) * (size_t)pa.max_chains);
+#pragma unroll
+        for (int q = 0; q < B9GW_MAX_VSHARDS / 32; ++q)
+            if ((need >> q & 1u) && r[q].y == step && r[q].w == step) {
+                pk[q] = __hiloint2double((int)r[q].z, (int)r[q].x);
+                need &= ~(1u << q);
+            }
+        if (!need) break;
+        if (t0 == ~0ULL) { ok = false; break; }
+        const unsigned long long now = b9gw::globaltimer_ns();
+        if (t0 == 0) t0 = now;
+        else if (now - t0 > pa.timeout_ns) { ok = false; break; }
+    }
+    const bool bad = __any_sync(FULL, !ok);
+    const double acc = add_shards_in_order(pk, V);
+    if (lane == 0) {
+        a.total[chain] = bad ? __longlong_as_double(0x7ff8000000000000LL) : acc;
+        if (bad) atomicExch(pa.status, 1);
+        pa.seq[chain] = step;
+        tk[a.n_shards] = 0;
+    }
+}
+
 // Called by one whole warp once the row values of local stars [s0, s1) of `chain` are
 // stored — all of them by this warp's lane 0, which also takes the tickets, so a ticket
-// releases them.  The warp that completes a virtual shard adds that shard's row values; with
-// all shards local, the warp that completes the chain's last shard adds the shards left to
-// right.  Which warp that is does not change any bit.  tickets[chain][k] counts finished
-// rows of local shard k, tickets[chain][n_shards] finished shards; each is reset by its last
-// user, ready for the next launch on the stream.
-__device__ void finish_rows(const LseArgs &a, long long chain, long long s0, long long s1, int lane) {
+// releases them.  The warp that completes a virtual shard adds that shard's row values; the
+// warp that completes the chain's last local shard finishes the chain: with all shards local
+// (and no peers) it adds the shards left to right; PEER, every completed shard is first
+// pushed to every rank's mailbox, and the finishing warp pulls all V from its own.  Which warp
+// that is does not change any bit.  tickets[chain][k] counts finished rows of local shard k,
+// tickets[chain][n_shards] finished shards; each is reset by its last user, ready for the
+// next launch on the stream.
+template <bool PEER>
+__device__ void finish_rows(const LseArgs &a, const PeerArgs &pa, long long chain, long long s0,
+                            long long s1, int lane) {
     const int V = 1 << a.vshift;
     const long long g0 = a.star0 + s0, g1 = a.star0 + s1;
     unsigned *tk = a.tickets + chain * (a.n_shards + 1);
     const double *rows = a.row_lse + chain * a.n_local;
+    // local shards that hold a star: with fewer stars than shards every shard holds 0 or 1
+    const unsigned nonempty = a.n_total < V ? (unsigned)a.n_local : (unsigned)a.n_shards;
+    const bool totals = PEER || (a.n_shards == V && a.total);
+    unsigned step = 0;
     bool all_done = false;
     for (long long v = (((g0 + 1) << a.vshift) + a.n_total - 1) / a.n_total - 1;    // shard holding g0
          v < a.first_shard + a.n_shards; ++v) {
@@ -162,38 +233,43 @@ __device__ void finish_rows(const LseArgs &a, long long chain, long long s0, lon
         // lane 0's acquire ordered the other warps' row values before the shuffle above; the
         // loads below bypass L1 (ld.cg), so no further fence is needed (each fence here is a
         // round trip on the kernel's serial tail, ~1.5 us apiece measured)
-        const double p = warp_ordered_sum(rows, lo - a.star0, hi - a.star0, lane);
+        const double p = warp_ordered_sum(rows, lo - a.star0, hi - a.star0, lane);   // in every lane
+        if constexpr (PEER) {
+            // lane d stores the packet into rank (rank + 1 + d)'s mailbox: remote peers first,
+            // self last.  The chain's counter moves only after every push of this launch.
+            step = *(volatile unsigned *)(pa.seq + chain) + 1u;
+            if (lane < pa.world) {
+                int peer = pa.rank + 1 + lane;
+                if (peer >= pa.world) peer -= pa.world;
+                b9gw::st_packet(pa.mail[peer] + ((size_t)(step & 1u) * V + (size_t)v) * (size_t)pa.max_chains
+                                    + (size_t)chain,
+                                (unsigned)__double2loint(p), (unsigned)__double2hiint(p), step);
+            }
+            __syncwarp();                                  // the pushes precede lane 0's ticket below
+        }
         done = 0;
         if (lane == 0) {
             a.partials[(long long)k * a.chains + chain] = p;
             tk[k] = 0;
-            if (a.n_shards == V && a.total) {
-                const unsigned nonempty = a.n_total < V ? (unsigned)a.n_total : (unsigned)V;
-                done = ticket_add(&tk[V], 1u) + 1u == nonempty;
-            }
+            if (totals) done = ticket_add(&tk[a.n_shards], 1u) + 1u == nonempty;
         }
         all_done |= __shfl_sync(FULL, done, 0) != 0;
     }
     if (!all_done) return;
-    double pk[B9GW_MAX_VSHARDS / 32];
+    if constexpr (PEER) {
+        pull_and_total(a, pa, chain, step, tk, lane);
+    } else {
+        double pk[B9GW_MAX_VSHARDS / 32];
 #pragma unroll
-    for (int q = 0; q < B9GW_MAX_VSHARDS / 32; ++q) {
-        const int u = lane + 32 * q;
-        pk[q] = u < V ? __ldcg(a.partials + (long long)u * a.chains + chain) : 0.0;   // empty shards hold +0
-    }
-    double acc = 0.0;
-#pragma unroll
-    for (int q = 0; q < B9GW_MAX_VSHARDS / 32; ++q) {
-        if (32 * q >= V) break;                            // warp-uniform
-#pragma unroll 8
-        for (int u = 0; u < 32; ++u) {                     // shuffles pipeline; only the adds are serial
-            const double pv = __shfl_sync(FULL, pk[q], u);
-            if (32 * q + u < V) acc = __dadd_rn(acc, pv);
+        for (int q = 0; q < B9GW_MAX_VSHARDS / 32; ++q) {
+            const int u = lane + 32 * q;
+            pk[q] = u < V ? __ldcg(a.partials + (long long)u * a.chains + chain) : 0.0;   // empty shards hold +0
         }
-    }
-    if (lane == 0) {
-        a.total[chain] = acc;
-        tk[V] = 0;
+        const double acc = add_shards_in_order(pk, V);
+        if (lane == 0) {
+            a.total[chain] = acc;
+            tk[V] = 0;
+        }
     }
 }
 
@@ -218,9 +294,10 @@ __device__ __forceinline__ double max_keep(double m, double v) { return v > m ? 
 // are inside libm's fast-path range the four exps run interleaved and branch-free,
 // otherwise the warp calls exp() itself.  Trip counts are warp-uniform; the padding columns
 // hold -inf, whose exp is +0 and changes no bit of the sum.
-template <int SRC>
+template <int SRC, bool PEER>
 __global__ void __launch_bounds__(STAGED_WARPS * 32, B9GW_STAGED_MIN_CTAS)
-lse_staged_kernel(const __grid_constant__ ExpConstants K, const __grid_constant__ LseArgs a) {
+lse_staged_kernel(const __grid_constant__ ExpConstants K, const __grid_constant__ LseArgs a,
+                  const __grid_constant__ PeerArgs pa) {
     extern __shared__ double sm[];        // [STAGED_WARPS][cap]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int n = a.cols, cap = a.cap;
@@ -229,7 +306,12 @@ lse_staged_kernel(const __grid_constant__ ExpConstants K, const __grid_constant_
     const long long chain = blockIdx.y;
     const long long s0 = ((long long)blockIdx.x * STAGED_WARPS + warp) * a.rpw;
     const long long s1 = s0 + a.rpw < a.n_local ? s0 + a.rpw : a.n_local;
-    if (blockIdx.x == 0 && warp == 0 && a.n_total < (1LL << a.vshift)) zero_empty_shards(a, chain, lane);
+    if (blockIdx.x == 0 && warp == 0 && a.n_total < (1LL << a.vshift)) {
+        zero_empty_shards(a, chain, lane);
+        if (PEER && a.n_local == 0)        // nothing local to finish: this warp does the cross-rank half
+            pull_and_total(a, pa, chain, *(volatile unsigned *)(pa.seq + chain) + 1u,
+                           a.tickets + chain * (a.n_shards + 1), lane);
+    }
 
     for (long long s = s0; s < s1; ++s) {
         // pass 1: fetch/generate once, park, max
@@ -286,17 +368,22 @@ lse_staged_kernel(const __grid_constant__ ExpConstants K, const __grid_constant_
         if (lane == 0) a.row_lse[chain * a.n_local + s] = r;
         __syncwarp();                     // the row's slice is reused by the next row
     }
-    if (s0 < s1) finish_rows(a, chain, s0, s1, lane);
+    if (s0 < s1) finish_rows<PEER>(a, pa, chain, s0, s1, lane);
 }
 
 // Longer rows: one warp per row, two passes over the source.
-template <int SRC>
-__global__ void __launch_bounds__(CTA_THREADS)
-lse_stream_kernel(const __grid_constant__ LseArgs a) {
+template <int SRC, bool PEER>
+__global__ void __launch_bounds__(CTA_THREADS, 4)
+lse_stream_kernel(const __grid_constant__ LseArgs a, const __grid_constant__ PeerArgs pa) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long long chain = blockIdx.y, cols = a.cols_ll;
     const long long s = (long long)blockIdx.x * STREAM_ROWS + warp;
-    if (blockIdx.x == 0 && warp == 0 && a.n_total < (1LL << a.vshift)) zero_empty_shards(a, chain, lane);
+    if (blockIdx.x == 0 && warp == 0 && a.n_total < (1LL << a.vshift)) {
+        zero_empty_shards(a, chain, lane);
+        if (PEER && a.n_local == 0)
+            pull_and_total(a, pa, chain, *(volatile unsigned *)(pa.seq + chain) + 1u,
+                           a.tickets + chain * (a.n_shards + 1), lane);
+    }
     if (s >= a.n_local) return;
     auto lse = [&](auto src) -> double {
         constexpr int B = 8;
@@ -319,7 +406,7 @@ lse_stream_kernel(const __grid_constant__ LseArgs a) {
     if constexpr (SRC == 0) r = lse(MatrixRow{a.x + (chain * a.n_local + s) * cols});
     else r = lse(GeneratedRow(chain * a.n_total + a.star0 + s, cols, a.inv_cols));
     if (lane == 0) a.row_lse[chain * a.n_local + s] = r;
-    finish_rows(a, chain, s, s + 1, lane);
+    finish_rows<PEER>(a, pa, chain, s, s + 1, lane);
 }
 
 __global__ void __launch_bounds__(256)
@@ -371,15 +458,15 @@ int rows_per_warp(long long rows) {
     return per_slot >= 8 ? 4 : per_slot >= 4 ? 2 : 1;
 }
 
-template <int SRC>
+template <int SRC, bool PEER = false>
 cudaError_t launch_lse(cudaStream_t st, const double *x, const b9gw::LseJob &j, double *row_lse,
-                       double *partials, double *total, unsigned *tickets) {
+                       double *partials, double *total, unsigned *tickets, const PeerArgs &pa = PeerArgs{}) {
     const int vshift = log2_of(j.V);
     LseArgs a;
     a.x = x;
     a.row_lse = row_lse;
     a.partials = partials;
-    a.total = j.n_shards == j.V ? total : nullptr;
+    a.total = PEER || j.n_shards == j.V ? total : nullptr;
     a.tickets = tickets;
     a.n_total = j.n_total;
     a.star0 = shard_lo(j.n_total, vshift, j.first_shard);
@@ -395,17 +482,18 @@ cudaError_t launch_lse(cudaStream_t st, const double *x, const b9gw::LseJob &j, 
     a.n_shards = j.n_shards;
     if (j.chains == 0 || j.n_shards == 0) return cudaSuccess;
     if (j.n_total == 0) {
+        // every shard on every rank is empty: the sum is +0 and no rank pushes or waits
         no_stars_kernel<<<32, 256, 0, st>>>(partials, (long long)j.n_shards * j.chains, a.total, j.chains);
     } else if (j.cols <= B9GW_LSE_STAGED_COLS) {
         a.cap = (int)((j.cols + 127) / 128 * 128);
         a.rpw = rows_per_warp(a.n_local * j.chains);
         const long long per_cta = (long long)STAGED_WARPS * a.rpw;
         const long long gx = a.n_local > 0 ? (a.n_local + per_cta - 1) / per_cta : 1;   // CTA 0 zeroes empty shards
-        lse_staged_kernel<SRC><<<dim3((unsigned)gx, (unsigned)j.chains), STAGED_WARPS * 32,
-                                 sizeof(double) * STAGED_WARPS * a.cap, st>>>(exp_constants(), a);
+        lse_staged_kernel<SRC, PEER><<<dim3((unsigned)gx, (unsigned)j.chains), STAGED_WARPS * 32,
+                                       sizeof(double) * STAGED_WARPS * a.cap, st>>>(exp_constants(), a, pa);
     } else {
         const long long gx = a.n_local > 0 ? (a.n_local + STREAM_ROWS - 1) / STREAM_ROWS : 1;
-        lse_stream_kernel<SRC><<<dim3((unsigned)gx, (unsigned)j.chains), CTA_THREADS, 0, st>>>(a);
+        lse_stream_kernel<SRC, PEER><<<dim3((unsigned)gx, (unsigned)j.chains), CTA_THREADS, 0, st>>>(a, pa);
     }
     return cudaGetLastError();
 }
@@ -497,6 +585,18 @@ int launch_lse_generated(cudaStream_t st, const LseJob &j, double *row_lse, doub
     if (rc != B9GW_OK) return rc;
     const cudaError_t e = launch_lse<1>(st, nullptr, j, row_lse, partials, total, tickets);
     if (e != cudaSuccess) return fail(B9GW_E_CUDA, "lse kernel launch", e);
+    return B9GW_OK;
+}
+
+int launch_lse_generated_step(cudaStream_t st, const LseJob &j, const PeerArgs &pa, double *row_lse,
+                              double *partials, double *total, unsigned *tickets) {
+    int rc = check_job(j);
+    if (rc != B9GW_OK) return rc;
+    if (j.chains > pa.max_chains) return fail(B9GW_E_ARG, "chains > the comm's max_chains");
+    if (j.V % pa.world || j.n_shards != j.V / pa.world || j.first_shard != pa.rank * j.n_shards)
+        return fail(B9GW_E_ARG, "the job's local shards are not this rank's");
+    const cudaError_t e = launch_lse<1, true>(st, nullptr, j, row_lse, partials, total, tickets, pa);
+    if (e != cudaSuccess) return fail(B9GW_E_CUDA, "fused lse step launch", e);
     return B9GW_OK;
 }
 

@@ -29,7 +29,7 @@
 // most one step ahead of a peer (it cannot finish step s+1 without the peer's
 // s+1 packets, which the peer sends only after its own step-s kernel — all its
 // reads of parity s — has retired), so parity s is never overwritten while read.
-// The step counter lives in device memory (one per CTA, bumped by the kernel), so
+// The step counter lives in device memory (one per chain, bumped by the kernel), so
 // a captured launch replays correctly from a CUDA graph.
 // A peer that never arrives costs `timeout_ns`, not a hang: the waiting thread
 // gives up, stores NaN and raises the comm's sticky status.
@@ -49,46 +49,28 @@ constexpr int STEP_THREADS = 256;          // 64 chains per CTA, 4 lanes per cha
 constexpr int PART_WARPS = 8;
 constexpr long long MAX_CHAINS = 1LL << 22;
 
-struct StepArgs {
-    uint4 *mail[B9GW_MAX_WORLD];           // mail[r]: rank r's mailbox as mapped in this process
-    unsigned *seq;                         // [grid] steps completed, per CTA
-    int *status;                           // sticky: 1 after any timeout
+using b9gw::PeerArgs;
+using b9gw::st_packet;
+using b9gw::ld_packet;
+using b9gw::globaltimer_ns;
+
+struct StepArgs : PeerArgs {
     const double *partial;                 // [V/world][chains]
     double *out;                           // [chains]
-    long long chains, max_chains;
-    unsigned long long timeout_ns;
-    int rank, world;
+    long long chains;
 };
-
-__device__ __forceinline__ void st_packet(uint4 *p, unsigned lo, unsigned hi, unsigned step) {
-    asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};"
-                 :: "l"(p), "r"(lo), "r"(step), "r"(hi), "r"(step) : "memory");
-}
-
-__device__ __forceinline__ uint4 ld_packet(const uint4 *p) {
-    uint4 r;
-    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];"
-                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
-    return r;
-}
-
-__device__ __forceinline__ unsigned long long globaltimer_ns() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-    return t;
-}
 
 template <int SLOTS>                       // V = 4 * SLOTS virtual shards
 __global__ void __launch_bounds__(STEP_THREADS)
 vshard_step_kernel(const StepArgs a) {
     constexpr int V = 4 * SLOTS;
-    const unsigned step = a.seq[blockIdx.x] + 1u;
-    const size_t parity_base = (size_t)(step & 1u) * V;
     const long long tid = (long long)blockIdx.x * STEP_THREADS + threadIdx.x;
     const long long chain = tid >> 2;
     const int q = (int)(tid & 3);
     const int lane = threadIdx.x & 31;
     const bool active = chain < a.chains;
+    const unsigned step = (active ? a.seq[chain] : 0u) + 1u;   // a chain's four lanes read it here,
+    const size_t parity_base = (size_t)(step & 1u) * V;        // before lane 3 moves it below
     bool ok = true;
     double val[SLOTS];
 #pragma unroll
@@ -148,9 +130,8 @@ vshard_step_kernel(const StepArgs a) {
         const bool chain_bad = ((bad >> (lane & ~3)) & 0xFu) != 0;
         a.out[chain] = chain_bad ? __longlong_as_double(0x7ff8000000000000LL) : acc;
         if (chain_bad) atomicExch(a.status, 1);
+        a.seq[chain] = step;               // after the shuffles above: the chain's lanes have read it
     }
-    __syncthreads();                       // every thread has read seq[] before it moves
-    if (threadIdx.x == 0) a.seq[blockIdx.x] = step;
 }
 
 // floor(v*n/V) for V a power of two (shift = log2 V), v <= V <= 128 and n <= 2^48: fits 64 bits.
@@ -199,7 +180,6 @@ bool vshards_ok(int V) { return V >= 4 && V <= B9GW_MAX_VSHARDS && (V & (V - 1))
 struct b9gw_comm {
     int device = -1, rank = 0, world = 1, V = 0;
     long long max_chains = 0;
-    unsigned grid = 0;
     uint4 *mail[B9GW_MAX_WORLD] = {};
     bool mapped[B9GW_MAX_WORLD] = {};
     unsigned *seq = nullptr;
@@ -210,26 +190,34 @@ struct b9gw_comm {
 
 namespace {
 
-int launch_step(b9gw_comm *c, const double *partial_dev, double *out_dev, long long chains,
-                cudaStream_t st) {
-    StepArgs a;
+PeerArgs peer_args(const b9gw_comm *c) {
+    PeerArgs a;
     for (int r = 0; r < B9GW_MAX_WORLD; ++r) a.mail[r] = c->mail[r];
     a.seq = c->seq;
     a.status = c->status;
-    a.partial = partial_dev;
-    a.out = out_dev;
-    a.chains = chains;
     a.max_chains = c->max_chains;
     a.timeout_ns = c->timeout_ns;
     a.rank = c->rank;
     a.world = c->world;
+    return a;
+}
+
+int launch_step(b9gw_comm *c, const double *partial_dev, double *out_dev, long long chains,
+                cudaStream_t st) {
+    StepArgs a;
+    static_cast<PeerArgs &>(a) = peer_args(c);
+    a.partial = partial_dev;
+    a.out = out_dev;
+    a.chains = chains;
+    if (chains == 0) return B9GW_OK;
+    const unsigned grid = (unsigned)((chains * 4 + STEP_THREADS - 1) / STEP_THREADS);
     switch (c->V) {
-        case 4:   vshard_step_kernel<1><<<c->grid, STEP_THREADS, 0, st>>>(a); break;
-        case 8:   vshard_step_kernel<2><<<c->grid, STEP_THREADS, 0, st>>>(a); break;
-        case 16:  vshard_step_kernel<4><<<c->grid, STEP_THREADS, 0, st>>>(a); break;
-        case 32:  vshard_step_kernel<8><<<c->grid, STEP_THREADS, 0, st>>>(a); break;
-        case 64:  vshard_step_kernel<16><<<c->grid, STEP_THREADS, 0, st>>>(a); break;
-        case 128: vshard_step_kernel<32><<<c->grid, STEP_THREADS, 0, st>>>(a); break;
+        case 4:   vshard_step_kernel<1><<<grid, STEP_THREADS, 0, st>>>(a); break;
+        case 8:   vshard_step_kernel<2><<<grid, STEP_THREADS, 0, st>>>(a); break;
+        case 16:  vshard_step_kernel<4><<<grid, STEP_THREADS, 0, st>>>(a); break;
+        case 32:  vshard_step_kernel<8><<<grid, STEP_THREADS, 0, st>>>(a); break;
+        case 64:  vshard_step_kernel<16><<<grid, STEP_THREADS, 0, st>>>(a); break;
+        case 128: vshard_step_kernel<32><<<grid, STEP_THREADS, 0, st>>>(a); break;
         default: return fail(B9GW_E_STATE, "comm has an unsupported shard count");
     }
     cudaError_t e = cudaGetLastError();
@@ -302,7 +290,6 @@ int b9gw_comm_create(int device, int rank, int world, int n_vshards, long long m
     c->world = world;
     c->V = n_vshards;
     c->max_chains = max_chains;
-    c->grid = (unsigned)((max_chains * 4 + STEP_THREADS - 1) / STEP_THREADS);
     {
         const size_t mail_bytes = (size_t)2 * n_vshards * (size_t)max_chains * sizeof(uint4);
         cudaIpcMemHandle_t h;
@@ -310,8 +297,8 @@ int b9gw_comm_create(int device, int rank, int world, int n_vshards, long long m
         static_assert(sizeof(cudaIpcMemHandle_t) == B9GW_IPC_HANDLE_BYTES, "handle size");
         CK(cudaMalloc(&c->mail[rank], mail_bytes));
         CK(cudaMemset(c->mail[rank], 0, mail_bytes));
-        CK(cudaMalloc(&c->seq, c->grid * sizeof(unsigned)));
-        CK(cudaMemset(c->seq, 0, c->grid * sizeof(unsigned)));
+        CK(cudaMalloc(&c->seq, max_chains * sizeof(unsigned)));
+        CK(cudaMemset(c->seq, 0, max_chains * sizeof(unsigned)));
         CK(cudaMalloc(&c->status, sizeof(int)));
         CK(cudaMemset(c->status, 0, sizeof(int)));
         CK(cudaDeviceSynchronize());       // zeroed before any peer can learn the handle
@@ -460,9 +447,25 @@ done:
     return rc;
 }
 
+int b9gw_lse_generated_step(b9gw_comm *c, long long n_stars_total, long long cols, long long chains,
+                            double *row_lse_dev, double *partial_dev, double *total_dev,
+                            void *workspace_dev, void *cuda_stream) {
+    if (!c) return fail(B9GW_E_ARG, "comm is null");
+    if (!c->connected) return fail(B9GW_E_STATE, "comm is not connected (call b9gw_comm_connect)");
+    if (chains < 0 || chains > c->max_chains) return fail(B9GW_E_ARG, "chains outside [0, max_chains]");
+    if (chains > 0 && (!row_lse_dev || !partial_dev || !total_dev || !workspace_dev))
+        return fail(B9GW_E_ARG, "null device buffer");
+    b9gw::DeviceGuard guard(c->device);
+    if (guard.rc() != B9GW_OK) return guard.rc();
+    const int per = c->V / c->world;
+    const b9gw::LseJob job{n_stars_total, cols, chains, c->V, c->rank * per, per};
+    return b9gw::launch_lse_generated_step((cudaStream_t)cuda_stream, job, peer_args(c), row_lse_dev,
+                                           partial_dev, total_dev, (unsigned *)workspace_dev);
+}
+
 int b9gw_sharded_step(b9gw_comm *c, long long n_stars_total, long long cols, long long chains,
-                      int warmup, int reps, double *total_host, float *us_step,
-                      float *us_lse_alone) {
+                      int warmup, int reps, double *total_host, double *total_fused_host,
+                      float *us_step, float *us_lse_alone, float *us_fused_step) {
     int rc = B9GW_OK, flag = 0;
     double *drow = nullptr, *dp = nullptr, *dout = nullptr;
     unsigned *dtk = nullptr;
@@ -515,6 +518,23 @@ int b9gw_sharded_step(b9gw_comm *c, long long n_stars_total, long long cols, lon
         CK(cudaEventElapsedTime(&ms, tm.a, tm.b));
         if (us_step) *us_step = ms * 1e3f / reps;
         if (total_host) CK(cudaMemcpy(total_host, dout, chains * sizeof(double), cudaMemcpyDeviceToHost));
+        CK(cudaMemset(dout, 0xff, chains * sizeof(double)));
+        {
+            const b9gw::PeerArgs pa = peer_args(c);
+            for (int i = 0; i < warmup + reps; ++i) {       // the same step as ONE kernel
+                if (i == warmup) {
+                    CK(cudaStreamSynchronize(st));
+                    CK(cudaEventRecord(tm.a, st));
+                }
+                if ((rc = b9gw::launch_lse_generated_step(st, job, pa, drow, dp, dout, dtk)) != B9GW_OK) goto done;
+            }
+        }
+        CK(cudaEventRecord(tm.b, st));
+        CK(cudaStreamSynchronize(st));
+        CK(cudaEventElapsedTime(&ms, tm.a, tm.b));
+        if (us_fused_step) *us_fused_step = ms * 1e3f / reps;
+        if (total_fused_host)
+            CK(cudaMemcpy(total_fused_host, dout, chains * sizeof(double), cudaMemcpyDeviceToHost));
         CK(cudaMemcpy(&flag, c->status, sizeof flag, cudaMemcpyDeviceToHost));
         if (flag) rc = fail(B9GW_E_TIMEOUT, "a peer did not arrive within the comm's timeout");
     }

@@ -13,7 +13,7 @@ from pathlib import Path
 import numpy as np
 
 LIB_PATH = Path(__file__).resolve().parent / "libb9_groundwork.so"
-ABI_VERSION = 4
+ABI_VERSION = 5
 DFMA_ILP, TRANS_ILP, THREADS = 8, 4, 256
 LSE_STAGED_COLS, MAX_WORLD, MAX_VSHARDS, IPC_HANDLE_BYTES = 1024, 16, 128, 64
 LSE_MAX_CHAINS = 65535
@@ -50,7 +50,8 @@ SYMBOLS = {
     "b9gw_comm_set_timeout_ms": (_i, [_vp, _i]),
     "b9gw_comm_status": (_i, [_vp, _pi, C.POINTER(_ull)]),
     "b9gw_allreduce_latency": (_i, [_vp, _ll, _i, _i, _pf, _pf]),
-    "b9gw_sharded_step": (_i, [_vp, _ll, _ll, _ll, _i, _i, _pd, _pf, _pf]),
+    "b9gw_lse_generated_step": (_i, [_vp, _ll, _ll, _ll, _vp, _vp, _vp, _vp, _vp]),
+    "b9gw_sharded_step": (_i, [_vp, _ll, _ll, _ll, _i, _i, _pd, _pd, _pf, _pf, _pf]),
     "b9gw_comm_destroy": (_i, [_vp]),
     "b9gw_vshard_total": (_i, [_i, _pd, _ll, _ll, _i, _pd, _pd]),
 }

@@ -151,13 +151,23 @@ class PeerComm:
         """b9gw_sharded_step: this rank's share of the star-sharded log-sum-exp job, then the
         cross-rank sum; total has the same bits on every rank and at every world size."""
         import numpy as np
-        total = np.empty(chains, dtype=np.float64)
-        a, b = C.c_float(), C.c_float()
+        total, fused = np.empty(chains, dtype=np.float64), np.empty(chains, dtype=np.float64)
+        a, b, f = C.c_float(), C.c_float(), C.c_float()
+        pd = C.POINTER(C.c_double)
         self._gw._ck(self._L.b9gw_sharded_step(self._h, n_stars_total, cols, chains, warmup, reps,
-                                               total.ctypes.data_as(C.POINTER(C.c_double)),
-                                               C.byref(a), C.byref(b)))
-        return {"total": total, "us_step": a.value, "us_lse_alone": b.value,
-                "launches": 3 * (warmup + reps)}
+                                               total.ctypes.data_as(pd), fused.ctypes.data_as(pd),
+                                               C.byref(a), C.byref(b), C.byref(f)))
+        return {"total": total, "total_fused": fused, "us_step": a.value, "us_lse_alone": b.value,
+                "us_fused_step": f.value, "launches": 4 * (warmup + reps)}
+
+    def lse_generated_step(self, n_stars_total: int, cols: int, chains: int, row_lse: torch.Tensor,
+                           partials: torch.Tensor, total: torch.Tensor, workspace: torch.Tensor) -> None:
+        """b9gw_lse_generated_step on the current stream: ONE kernel = this rank's share of the
+        log-sum-exp job + the cross-rank sum.  Buffers are the caller's CUDA tensors (workspace
+        zero before the first launch)."""
+        self._gw._ck(self._L.b9gw_lse_generated_step(
+            self._h, n_stars_total, cols, chains, row_lse.data_ptr(), partials.data_ptr(),
+            total.data_ptr(), workspace.data_ptr(), self._stream()))
 
     def status(self) -> dict:
         """Synchronises; raises GroundworkError(E_TIMEOUT) if any step gave up waiting."""

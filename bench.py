@@ -172,15 +172,16 @@ def _vshard_section(gw, rank: int, world: int, local: int, warmup: int, steps: i
 def _sharded_step(gw, comm, rank: int, world: int, local: int, warmup: int, steps: int) -> tuple[dict, int]:
     """Star sharding with real work per rank (still NOT a likelihood: the synthetic generator).
     A fixed job — 10 000 stars x 1024 terms x `chains` chains — is cut into the 64 virtual shards;
-    each rank runs the fixed-order log-sum-exp of its own 64/W shards and then the cross-rank sum:
-    two launches per step.  Strong scaling: the job does not grow with W.  The total's bits are
+    each rank runs the fixed-order log-sum-exp of its own 64/W shards and then the cross-rank sum —
+    as two launches, and as ONE kernel with the sum fused into the LSE kernel's tail (packets pushed
+    by the warp that completes a shard).  Strong scaling: the job does not grow with W.  The total's bits are
     asserted equal, on every rank, to those the rank gets alone from all 64 shards."""
     import numpy as np
     import torch
     import torch.distributed as dist
 
     n_stars, cols, V = 10_000, 1_024, comm.n_vshards
-    out, launches = {"n_stars": n_stars, "cols": cols, "scaling": "strong", "launches_per_step": 2}, 0
+    out, launches = {"n_stars": n_stars, "cols": cols, "scaling": "strong"}, 0
     for chains in (16, 128):
         r = comm.sharded_step(n_stars, cols, chains, warmup=max(warmup, 3), reps=steps)
         launches += r["launches"]
@@ -188,14 +189,17 @@ def _sharded_step(gw, comm, rank: int, world: int, local: int, warmup: int, step
         launches += 1
         if not (r["total"].view(np.int64) == alone.view(np.int64)).all():
             raise SystemExit(f"rank {rank}: the {world}-rank sharded step differs in bits from the 1-rank job")
-        us = torch.tensor([r["us_step"], r["us_lse_alone"]], device=f"cuda:{local}")
+        if not (r["total_fused"].view(np.int64) == alone.view(np.int64)).all():
+            raise SystemExit(f"rank {rank}: the one-kernel step differs in bits from the 1-rank job")
+        us = torch.tensor([r["us_step"], r["us_lse_alone"], r["us_fused_step"]], device=f"cuda:{local}")
         if world > 1:
             dist.all_reduce(us, op=dist.ReduceOp.MAX)   # device-timed, max over ranks
             dist.barrier()
-        sec = us[0].item() * 1e-6
+        sec = us[2].item() * 1e-6
         out[f"chains_{chains}"] = {
-            "us_step": round(us[0].item(), 2), "us_lse_share_alone": round(us[1].item(), 2),
-            "gterms_per_s_whole_job": round(n_stars * cols * chains / sec * 1e-9, 1),
+            "us_fused_step_1_launch": round(us[2].item(), 2), "us_step_2_launches": round(us[0].item(), 2),
+            "us_lse_share_alone": round(us[1].item(), 2),
+            "gterms_per_s_whole_job_fused": round(n_stars * cols * chains / sec * 1e-9, 1),
             "bits_equal_world_1": True}
     return out, launches
 

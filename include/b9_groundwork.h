@@ -1,5 +1,5 @@
 /*
- * b9_groundwork.h — C-ABI of libb9_groundwork.so  (ABI version 4)
+ * b9_groundwork.h — C-ABI of libb9_groundwork.so  (ABI version 5)
  *
  * STATUS: the BASE-9 hot path is BLOCKED.  /root/reference is a
  * 4-line relocation notice (/root/reference/README.md:1-4); the base-cpp source
@@ -311,19 +311,40 @@ int b9gw_allreduce_latency(b9gw_comm *comm, long long chains, int warmup,
                            int reps, float *us_stream, float *us_graph);
 
 /*
- * A star-sharded step, end to end and timed: b9gw_lse_generated_shards over this
- * rank's V/world shards of an (n_stars_total x cols)-term, `chains`-chain job,
- * then b9gw_ordered_allreduce of the [V/world][chains] partials it wrote — two
- * launches per step, back to back on one private stream, no host work between
- * them.  total_host (may be NULL) receives total[chains] of the last step: the
- * same bits on every rank AND at every world size, because no W enters the
- * definition of either kernel's result.  us_lse_alone: the first launch alone
- * (`reps` after `warmup`); us_step: both.  CUDA events on that stream; every rank
- * must call with the same arguments.  Same limits as b9gw_lse_generated_shards.
+ * The star-sharded step as ONE kernel: b9gw_lse_generated_shards over this
+ * rank's V/world shards of the job, with the cross-rank sum fused into its tail.
+ * The warp that completes a local shard stores that shard's P straight into
+ * every rank's mailbox (the same 16-byte self-flagging packets as above); the
+ * warp that completes a chain's last local shard then polls the chain's V slots
+ * in its own mailbox and adds them left to right into total_dev[chain] — while
+ * other chains' rows are still being evaluated on the rest of the GPU.  A rank
+ * whose shards hold no star at all still takes part (it only pulls).  Same
+ * buffers, limits and workspace as b9gw_lse_generated_shards (the local shard
+ * range is the comm's); same ordering rules, step counters, timeout behaviour
+ * and bits as b9gw_ordered_allreduce, with which it may be freely mixed on one
+ * comm.  total_dev [chains] is written on every rank.
+ */
+int b9gw_lse_generated_step(b9gw_comm *comm, long long n_stars_total, long long cols,
+                            long long chains, double *row_lse_dev, double *partial_dev,
+                            double *total_dev, void *workspace_dev, void *cuda_stream);
+
+/*
+ * A star-sharded step, end to end and timed, two ways on one private stream
+ * (CUDA events, `reps` after `warmup`, no host work inside a step):
+ *   us_lse_alone  : b9gw_lse_generated_shards over this rank's V/world shards of
+ *                   an (n_stars_total x cols)-term, `chains`-chain job;
+ *   us_step       : that launch, then b9gw_ordered_allreduce of the partials it
+ *                   wrote — two launches per step;
+ *   us_fused_step : b9gw_lse_generated_step — one launch per step.
+ * total_host / total_fused_host (may be NULL) receive total[chains] of the last
+ * two-launch / fused step: the same bits as each other, on every rank AND at
+ * every world size, because no W enters the definition of any kernel's result.
+ * Every rank must call with the same arguments.
  */
 int b9gw_sharded_step(b9gw_comm *comm, long long n_stars_total, long long cols,
                       long long chains, int warmup, int reps, double *total_host,
-                      float *us_step, float *us_lse_alone);
+                      double *total_fused_host, float *us_step, float *us_lse_alone,
+                      float *us_fused_step);
 
 /* Unmaps the peers and frees the mailbox.  The caller must make sure (barrier)
  * that no peer is still inside a step. */

@@ -34,7 +34,7 @@ struct Shared {
     char handles[B9GW_MAX_WORLD][B9GW_IPC_HANDLE_BYTES];
     int arrived, generation;
     int ok[B9GW_MAX_WORLD];
-    float us_stream[B9GW_MAX_WORLD], us_graph[B9GW_MAX_WORLD], us_sharded[B9GW_MAX_WORLD];
+    float us_stream[B9GW_MAX_WORLD], us_graph[B9GW_MAX_WORLD], us_sharded[B9GW_MAX_WORLD], us_fused[B9GW_MAX_WORLD];
 };
 
 void barrier(Shared *s, int world) {                    // sense-reversing, across processes
@@ -116,9 +116,10 @@ int run_rank(int rank, int world, Shared *sh) {
         // a star-sharded step end to end (this rank's shards' log-sum-exp, then the cross-rank sum)
         // against the same job done by this rank alone from all V shards in one launch
         const long long sn = 3001, sc = 160, sch = 9;
-        std::vector<double> stepped(sch), alone(sch);
+        std::vector<double> stepped(sch), fused(sch), alone(sch);
         float us_lse = 0;
-        CHECK(b9gw_sharded_step(comm, sn, sc, sch, 2, 10, stepped.data(), &sh->us_sharded[rank], &us_lse));
+        CHECK(b9gw_sharded_step(comm, sn, sc, sch, 2, 10, stepped.data(), fused.data(), &sh->us_sharded[rank],
+                                &us_lse, &sh->us_fused[rank]));
         void *d_rows, *d_p, *d_t, *d_ws;
         CHECK(b9gw_dev_malloc(rank, sch * sn * 8, &d_rows));
         CHECK(b9gw_dev_malloc(rank, sch * V * 8, &d_p));
@@ -128,6 +129,7 @@ int run_rank(int rank, int world, Shared *sh) {
                                         (double *)d_t, d_ws, nullptr));
         CHECK(b9gw_memcpy_d2h(rank, alone.data(), d_t, sch * 8));
         ok &= memcmp(stepped.data(), alone.data(), sch * 8) == 0;
+        ok &= memcmp(fused.data(), alone.data(), sch * 8) == 0;
         b9gw_dev_free(rank, d_rows);
         b9gw_dev_free(rank, d_p);
         b9gw_dev_free(rank, d_t);
@@ -165,15 +167,16 @@ int main(int argc, char **argv) {
         waitpid(p, &st, 0);
         bad |= !WIFEXITED(st) || WEXITSTATUS(st) != 0;
     }
-    float us_s = 0, us_g = 0, us_sh = 0;
+    float us_s = 0, us_g = 0, us_sh = 0, us_fu = 0;
     for (int r = 0; r < world; ++r) {
         bad |= !sh->ok[r];
         us_s = sh->us_stream[r] > us_s ? sh->us_stream[r] : us_s;
         us_g = sh->us_graph[r] > us_g ? sh->us_graph[r] : us_g;
         us_sh = sh->us_sharded[r] > us_sh ? sh->us_sharded[r] : us_sh;
+        us_fu = sh->us_fused[r] > us_fu ? sh->us_fused[r] : us_fu;
     }
     printf("{\"world\": %d, \"bits_equal_checker\": %s, \"steps\": %d, \"us_stream_max\": %.2f, "
-           "\"us_graph_max\": %.2f, \"sharded_step_us_max\": %.2f, \"driver\": \"C++ (no Python, no NCCL)\"}\n",
-           world, bad ? "false" : "true", STEPS, us_s, us_g, us_sh);
+           "\"us_graph_max\": %.2f, \"sharded_step_us_max\": %.2f, \"fused_step_us_max\": %.2f, \"driver\": \"C++ (no Python, no NCCL)\"}\n",
+           world, bad ? "false" : "true", STEPS, us_s, us_g, us_sh, us_fu);
     return bad;
 }

@@ -86,6 +86,13 @@ def main():
         step = comm.sharded_step(sn, sc, sch, warmup=2, reps=10)
         alone = gw.lse_generated_shards(sn, sc, sch, V, 0, V, local)["total"]
         assert (step["total"].view(np.int64) == alone.view(np.int64)).all(), f"rank {rank}: sharded step"
+        assert (step["total_fused"].view(np.int64) == alone.view(np.int64)).all(), f"rank {rank}: fused step"
+        # fewer stars than shards: most ranks own no star at all and only pull
+        tiny = comm.sharded_step(5, 40, 3, warmup=1, reps=3)
+        tiny_alone = gw.lse_generated_shards(5, 40, 3, V, 0, V, local)["total"]
+        assert (tiny["total"].view(np.int64) == tiny_alone.view(np.int64)).all()
+        assert (tiny["total_fused"].view(np.int64) == tiny_alone.view(np.int64)).all(), f"rank {rank}: tiny fused"
+        report["fused_step_us"] = round(step["us_fused_step"], 2)
         flat = gw.lse_generated(sch * sn, sc, local)["row_lse"].reshape(sch, sn)
         assert (ref.vshard_total(flat, V)[1].view(np.int64) == alone.view(np.int64)).all()
         report["sharded_step_bits_equal_world_1"] = True

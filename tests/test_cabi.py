@@ -90,7 +90,8 @@ def test_product_package_never_touches_the_checker():
         assert "groundwork_ref" not in text and "tests._ref" not in text and "from tests" not in text, py
 
 
-@pytest.mark.parametrize("kernel", ["lse_staged_kernelILi0", "lse_staged_kernelILi1"])
+@pytest.mark.parametrize("kernel", ["lse_staged_kernelILi0ELb0", "lse_staged_kernelILi1ELb0",
+                                    "lse_staged_kernelILi1ELb1"])
 def test_pass2_exp_chains_stay_interleaved_in_the_sass(built, kernel):
     """The four exps a lane evaluates per pass-2 iteration must be interleaved in the SASS (one
     dependent DFMA chain per warp cannot feed the FP64 pipe); ptxas once serialised them after an

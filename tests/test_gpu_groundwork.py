@@ -335,8 +335,38 @@ def test_sharded_step_world_1(gw, ref):
     with vshards.PeerComm(0, 0, 1, V, max_chains=16) as comm:
         r = comm.sharded_step(n_total, cols, chains, warmup=2, reps=5)
         assert (bits(r["total"]) == bits(want)).all()
-        assert 0 < r["us_lse_alone"] <= r["us_step"] * 1.5
-        assert comm.status()["steps"] == 7
+        assert (bits(r["total_fused"]) == bits(want)).all(), "the one-kernel step differs from the two-launch step"
+        assert 0 < r["us_lse_alone"] <= r["us_step"] * 1.5 and r["us_fused_step"] > 0
+        assert comm.status()["steps"] == 14          # 7 two-launch steps + 7 fused ones on chain 0
+
+
+@pytest.mark.parametrize("n_total,cols,chains,V", [(1003, 96, 5, 64), (37, 50, 4, 64), (700, 1500, 2, 16),
+                                                   (0, 8, 3, 64), (5000, 1024, 33, 128)])
+def test_fused_step_world_1_mixes_with_the_two_launch_step(gw, ref, n_total, cols, chains, V):
+    """b9gw_lse_generated_step through caller-held device tensors, alternating with
+    shard_partials + allreduce on the same comm (shared mailbox parity and step counters)."""
+    import torch
+    from base_b200 import vshards
+    flat = gw.lse_generated(chains * n_total, cols, 0)["row_lse"].reshape(chains, n_total)
+    wantP, want = ref.vshard_total(flat, V)
+    dev = torch.device("cuda", 0)
+    with vshards.PeerComm(0, 0, 1, V, max_chains=64) as comm:
+        rows = torch.empty(chains, max(n_total, 1), dtype=torch.float64, device=dev)
+        P = torch.empty(V, chains, dtype=torch.float64, device=dev)
+        tot = torch.full((chains,), float("nan"), dtype=torch.float64, device=dev)
+        work = torch.zeros(gw.lib().b9gw_lse_workspace_bytes(chains, V) // 4, dtype=torch.int32, device=dev)
+        vals = torch.from_numpy(flat).to(dev)
+        for rep in range(3):
+            tot.fill_(float("nan"))
+            comm.lse_generated_step(n_total, cols, chains, rows, P, tot, work)
+            torch.cuda.synchronize()
+            assert (bits(tot.cpu().numpy()) == bits(want)).all(), rep
+            assert (bits(P.cpu().numpy()) == bits(wantP)).all(), rep
+            assert not work.any()
+            two = comm.allreduce(comm.shard_partials(vals, n_total)) if n_total else None
+            if two is not None:
+                assert (bits(two.cpu().numpy()) == bits(want)).all(), rep
+        assert comm.status()["steps"] == (6 if n_total else 0)
 
 
 def test_smoke_entry_point(gw):

@@ -53,7 +53,7 @@ def fast_path_runs(lib: str | Path, kernel_substr: str) -> list[tuple[str, int]]
 
 if __name__ == "__main__":
     lib = sys.argv[1] if len(sys.argv) > 1 else Path(__file__).resolve().parent.parent / "base_b200" / "libb9_groundwork.so"
-    for k in ("lse_staged_kernelILi0", "lse_staged_kernelILi1"):
+    for k in ("lse_staged_kernelILi0ELb0", "lse_staged_kernelILi1ELb0", "lse_staged_kernelILi1ELb1"):
         runs = fast_path_runs(lib, k)
         print(k, "longest run", max(n for _, n in runs), "of", sum(n for _, n in runs), "DFMAs")
         print("  ", " ".join(f"{r}x{n}" if n > 1 else r for r, n in runs))
