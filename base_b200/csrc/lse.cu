@@ -57,8 +57,13 @@ constexpr int CTA_THREADS = 256;
 // thread) and un-interleaves the four exps of pass 2 into 1 + 1 + 2 dependent chains; shared
 // memory allows 6 CTAs per SM anyway.  With the bound it keeps all four chains interleaved
 // (62 registers): 304 instead of 330 us at 160 000 x 1024 (gpurun A/B, profiles/r03_*).
+// The fused (PEER) instantiation carries the mailbox tail as well and spills at 64 registers;
+// it is bounded by the 6 CTAs shared memory allows at 1024 columns.
 #ifndef B9GW_STAGED_MIN_CTAS
 #define B9GW_STAGED_MIN_CTAS 8
+#endif
+#ifndef B9GW_STAGED_MIN_CTAS_PEER
+#define B9GW_STAGED_MIN_CTAS_PEER 6
 #endif
 constexpr int STAGED_WARPS = B9GW_STAGED_WARPS;   // staged rows in flight per CTA, one warp each
 constexpr int PASS2_TERMS = B9GW_PASS2_TERMS;     // terms a lane exponentiates per iteration (divides 128 / 32 * k)
@@ -135,7 +140,15 @@ struct LseArgs {
     long long n_local, n_total, star0, chains, cols_ll;
     double inv_cols;
     int cols, cap, rpw, vshift, first_shard, n_shards;
+#ifdef B9GW_DIAG
+    int diag;                              // tools/fused_diag.py: 1 = do not wait for remote shards, 2 = do not push to peers
+#endif
 };
+
+#ifdef B9GW_DIAG
+__device__ unsigned long long g_diag[8 * 16 * 4];   // [step % 8][chain < 16]: enter pull, lane 0 has its packets, total stored, chain's first CTA start
+#define DIAG_SLOT(step, chain) (((step) & 7u) * 64 + (chain) * 4)
+#endif
 
 // Shards 32q + lane, q = 0.., held one per lane in pk[q] (empty shards: +0), added strictly left
 // to right starting from +0.  The shuffles pipeline; only the adds are serial.
@@ -169,10 +182,19 @@ __device__ void pull_and_total(const LseArgs &a, const PeerArgs &pa, long long c
         const int u = lane + 32 * q;
         pk[q] = 0.0;
         if (u < V && shard_lo(a.n_total, a.vshift, u + 1) > shard_lo(a.n_total, a.vshift, u)) need |= 1u << q;
+#ifdef B9GW_DIAG
+        if ((a.diag & 1) && (u < a.first_shard || u >= a.first_shard + a.n_shards)) need &= ~(1u << q);
+#endif
     }
+#ifdef B9GW_DIAG
+    if (lane == 0 && chain < 16) g_diag[DIAG_SLOT(step, chain)] = b9gw::globaltimer_ns();
+#endif
+    // The warp stays converged: it leaves the loop as a whole, on a vote.  (Lanes leaving one by
+    // one made everything after the loop — 128 shuffles — run ~12x slower on the rank that had
+    // to wait: profiles/r03_groundwork.md.)
     bool ok = true;
     unsigned long long t0 = *(volatile int *)pa.status ? ~0ULL : 0;   // a comm that timed out stays out of step
-    while (need) {
+    for (;;) {
         uint4 r[B9GW_MAX_VSHARDS / 32];
 #pragma unroll
         for (int q = 0; q < B9GW_MAX_VSHARDS / 32; ++q)
@@ -183,15 +205,24 @@ __device__ void pull_and_total(const LseArgs &a, const PeerArgs &pa, long long c
                 pk[q] = __hiloint2double((int)r[q].z, (int)r[q].x);
                 need &= ~(1u << q);
             }
-        if (!need) break;
-        if (t0 == ~0ULL) { ok = false; break; }
-        const unsigned long long now = b9gw::globaltimer_ns();
-        if (t0 == 0) t0 = now;
-        else if (now - t0 > pa.timeout_ns) { ok = false; break; }
+        if (__all_sync(FULL, need == 0)) break;
+        bool expired = t0 == ~0ULL;
+        if (!expired) {
+            const unsigned long long now = b9gw::globaltimer_ns();
+            if (t0 == 0) t0 = now;
+            else expired = now - t0 > pa.timeout_ns;
+        }
+        if (__any_sync(FULL, expired)) { ok = need == 0; break; }
     }
     const bool bad = __any_sync(FULL, !ok);
+#ifdef B9GW_DIAG
+    if (lane == 0 && chain < 16) g_diag[DIAG_SLOT(step, chain) + 1] = b9gw::globaltimer_ns();
+#endif
     const double acc = add_shards_in_order(pk, V);
     if (lane == 0) {
+#ifdef B9GW_DIAG
+        if (chain < 16) g_diag[DIAG_SLOT(step, chain) + 2] = b9gw::globaltimer_ns();
+#endif
         a.total[chain] = bad ? __longlong_as_double(0x7ff8000000000000LL) : acc;
         if (bad) atomicExch(pa.status, 1);
         pa.seq[chain] = step;
@@ -218,35 +249,24 @@ __device__ void finish_rows(const LseArgs &a, const PeerArgs &pa, long long chai
     // local shards that hold a star: with fewer stars than shards every shard holds 0 or 1
     const unsigned nonempty = a.n_total < V ? (unsigned)a.n_local : (unsigned)a.n_shards;
     const bool totals = PEER || (a.n_shards == V && a.total);
-    unsigned step = 0;
     bool all_done = false;
-    for (long long v = (((g0 + 1) << a.vshift) + a.n_total - 1) / a.n_total - 1;    // shard holding g0
-         v < a.first_shard + a.n_shards; ++v) {
+    unsigned long long completed = 0;      // bit i: the i-th shard this warp touched was completed by it
+    int touched = 0;                       // <= s1 - s0 <= 64 (every touched shard holds one of our stars)
+    const long long v_first = (((g0 + 1) << a.vshift) + a.n_total - 1) / a.n_total - 1;   // shard holding g0
+    for (long long v = v_first; v < a.first_shard + a.n_shards; ++v) {
         const long long lo = shard_lo(a.n_total, a.vshift, v), hi = shard_lo(a.n_total, a.vshift, v + 1);
         if (lo >= g1) break;
         if (hi <= lo) continue;                            // empty shard (n_total < V)
         const unsigned mine = (unsigned)((hi < g1 ? hi : g1) - (lo > g0 ? lo : g0));
-        const int k = (int)(v - a.first_shard);
+        const int k = (int)(v - a.first_shard), i = touched++;
         unsigned done = 0;
         if (lane == 0) done = ticket_add(&tk[k], mine) + mine == (unsigned)(hi - lo);
         if (!__shfl_sync(FULL, done, 0)) continue;
         // lane 0's acquire ordered the other warps' row values before the shuffle above; the
         // loads below bypass L1 (ld.cg), so no further fence is needed (each fence here is a
         // round trip on the kernel's serial tail, ~1.5 us apiece measured)
-        const double p = warp_ordered_sum(rows, lo - a.star0, hi - a.star0, lane);   // in every lane
-        if constexpr (PEER) {
-            // lane d stores the packet into rank (rank + 1 + d)'s mailbox: remote peers first,
-            // self last.  The chain's counter moves only after every push of this launch.
-            step = *(volatile unsigned *)(pa.seq + chain) + 1u;
-            if (lane < pa.world) {
-                int peer = pa.rank + 1 + lane;
-                if (peer >= pa.world) peer -= pa.world;
-                b9gw::st_packet(pa.mail[peer] + ((size_t)(step & 1u) * V + (size_t)v) * (size_t)pa.max_chains
-                                    + (size_t)chain,
-                                (unsigned)__double2loint(p), (unsigned)__double2hiint(p), step);
-            }
-            __syncwarp();                                  // the pushes precede lane 0's ticket below
-        }
+        const double p = warp_ordered_sum(rows, lo - a.star0, hi - a.star0, lane);
+        completed |= 1ULL << i;
         done = 0;
         if (lane == 0) {
             a.partials[(long long)k * a.chains + chain] = p;
@@ -254,6 +274,37 @@ __device__ void finish_rows(const LseArgs &a, const PeerArgs &pa, long long chai
             if (totals) done = ticket_add(&tk[a.n_shards], 1u) + 1u == nonempty;
         }
         all_done |= __shfl_sync(FULL, done, 0) != 0;
+    }
+    unsigned step = 0;
+    if constexpr (PEER) {
+        // The completed shards' P are pushed after the warp's last ticket.  Nothing needs them
+        // earlier — the finishing warp polls for them like for any peer's — and the chain's
+        // counter cannot move before every push of this launch has landed, because moving it
+        // waits for all V packets.  (Measured alternatives, profiles/r03_groundwork.md: pushing
+        // inside the loop, and fetching the counter when the warp starts, were both slower.)
+        // Lane d stores into rank (rank + 1 + d)'s mailbox: remote peers first, self last.
+        if (completed) {
+            __syncwarp();                                  // lane 0's partials[] stores, read below by all
+            step = *(volatile unsigned *)(pa.seq + chain) + 1u;
+            int i = 0;
+            for (long long v = v_first; i < touched && completed >> i; ++v) {
+                if (shard_lo(a.n_total, a.vshift, v + 1) <= shard_lo(a.n_total, a.vshift, v)) continue;
+                if (completed >> i++ & 1ULL) {
+                    const double p = a.partials[(v - a.first_shard) * a.chains + chain];
+                    bool push = lane < pa.world;
+#ifdef B9GW_DIAG
+                    if (a.diag & 2) push = lane == pa.world - 1;   // self only
+#endif
+                    if (push) {
+                        int peer = pa.rank + 1 + lane;
+                        if (peer >= pa.world) peer -= pa.world;
+                        b9gw::st_packet(pa.mail[peer] + ((size_t)(step & 1u) * V + (size_t)v) * (size_t)pa.max_chains
+                                            + (size_t)chain,
+                                        (unsigned)__double2loint(p), (unsigned)__double2hiint(p), step);
+                    }
+                }
+            }
+        }
     }
     if (!all_done) return;
     if constexpr (PEER) {
@@ -295,7 +346,7 @@ __device__ __forceinline__ double max_keep(double m, double v) { return v > m ? 
 // otherwise the warp calls exp() itself.  Trip counts are warp-uniform; the padding columns
 // hold -inf, whose exp is +0 and changes no bit of the sum.
 template <int SRC, bool PEER>
-__global__ void __launch_bounds__(STAGED_WARPS * 32, B9GW_STAGED_MIN_CTAS)
+__global__ void __launch_bounds__(STAGED_WARPS * 32, PEER ? B9GW_STAGED_MIN_CTAS_PEER : B9GW_STAGED_MIN_CTAS)
 lse_staged_kernel(const __grid_constant__ ExpConstants K, const __grid_constant__ LseArgs a,
                   const __grid_constant__ PeerArgs pa) {
     extern __shared__ double sm[];        // [STAGED_WARPS][cap]
@@ -306,6 +357,10 @@ lse_staged_kernel(const __grid_constant__ ExpConstants K, const __grid_constant_
     const long long chain = blockIdx.y;
     const long long s0 = ((long long)blockIdx.x * STAGED_WARPS + warp) * a.rpw;
     const long long s1 = s0 + a.rpw < a.n_local ? s0 + a.rpw : a.n_local;
+#ifdef B9GW_DIAG
+    if (PEER && blockIdx.x == 0 && threadIdx.x == 0 && chain < 16)
+        g_diag[DIAG_SLOT(*(volatile unsigned *)(pa.seq + chain) + 1u, chain) + 3] = b9gw::globaltimer_ns();
+#endif
     if (blockIdx.x == 0 && warp == 0 && a.n_total < (1LL << a.vshift)) {
         zero_empty_shards(a, chain, lane);
         if (PEER && a.n_local == 0)        // nothing local to finish: this warp does the cross-rank half
@@ -480,6 +535,10 @@ cudaError_t launch_lse(cudaStream_t st, const double *x, const b9gw::LseJob &j, 
     a.vshift = vshift;
     a.first_shard = j.first_shard;
     a.n_shards = j.n_shards;
+#ifdef B9GW_DIAG
+    a.diag = 0;
+    if (const char *e = getenv("B9GW_DIAG_FLAGS")) a.diag = atoi(e);
+#endif
     if (j.chains == 0 || j.n_shards == 0) return cudaSuccess;
     if (j.n_total == 0) {
         // every shard on every rank is empty: the sum is +0 and no rank pushes or waits
@@ -617,6 +676,17 @@ int b9gw_lse_generated(int device, long long rows, long long cols, int n_vshards
     return run_lse<1>(device, nullptr, rows, cols, n_vshards, warmup, reps, row_lse_host,
                       partials_host, total_host, ms_per_launch);
 }
+
+#ifdef B9GW_DIAG
+int b9gw_diag_dump(int device, long long chains, unsigned long long *out) {   // tools/fused_diag.py only
+    b9gw::DeviceGuard guard(device);
+    if (guard.rc() != B9GW_OK) return guard.rc();
+    cudaDeviceSynchronize();
+    (void)chains;
+    cudaError_t e = cudaMemcpyFromSymbol(out, g_diag, sizeof(g_diag));
+    return e == cudaSuccess ? B9GW_OK : fail(B9GW_E_CUDA, "cudaMemcpyFromSymbol", e);
+}
+#endif
 
 long long b9gw_lse_workspace_bytes(long long chains, int n_shards) {
     if (chains < 0 || chains > B9GW_LSE_MAX_CHAINS || n_shards < 0 || n_shards > B9GW_MAX_VSHARDS)

@@ -76,6 +76,8 @@ vshard_step_kernel(const StepArgs a) {
 #pragma unroll
     for (int i = 0; i < SLOTS; ++i) val[i] = 0.0;
 
+    const uint4 *mine = nullptr;
+    unsigned long long t0 = 0;
     if (active) {
         // ---- push: own shards to every rank, remote peers first, self last
         const int per = V / a.world, first = a.rank * per;
@@ -90,12 +92,17 @@ vshard_step_kernel(const StepArgs a) {
             }
         }
         // ---- pull: shards q*SLOTS .. q*SLOTS+SLOTS-1 of this chain, from the local mailbox
-        const uint4 *mine = a.mail[a.rank] + (parity_base + (size_t)q * SLOTS) * (size_t)a.max_chains
-                            + (size_t)chain;
+        mine = a.mail[a.rank] + (parity_base + (size_t)q * SLOTS) * (size_t)a.max_chains + (size_t)chain;
         // a comm that has already timed out is out of step with its peers for good: do not
         // spend another timeout per launch on it
-        unsigned long long t0 = *(volatile int *)a.status ? ~0ULL : 0;
-        for (;;) {
+        t0 = *(volatile int *)a.status ? ~0ULL : 0;
+    }
+    // The warp polls as a whole and leaves the loop on a vote, so that it is still converged
+    // for the shuffles below (lanes leaving one by one made everything behind a poll loop run
+    // an order of magnitude slower in the fused kernel: profiles/r03_groundwork.md).
+    bool got = !active;
+    for (;;) {
+        if (!got) {
             uint4 r[SLOTS];
 #pragma unroll
             for (int i = 0; i < SLOTS; ++i) r[i] = ld_packet(mine + (size_t)i * a.max_chains);
@@ -105,13 +112,20 @@ vshard_step_kernel(const StepArgs a) {
             if (ready) {
 #pragma unroll
                 for (int i = 0; i < SLOTS; ++i) val[i] = __hiloint2double((int)r[i].z, (int)r[i].x);
-                break;
+                got = true;
             }
-            if (t0 == ~0ULL) { ok = false; break; }
-            const unsigned long long now = globaltimer_ns();
-            if (t0 == 0) t0 = now;
-            else if (now - t0 > a.timeout_ns) { ok = false; break; }
         }
+        if (__all_sync(FULL, got)) break;
+        bool expired = false;
+        if (!got) {
+            expired = t0 == ~0ULL;
+            if (!expired) {
+                const unsigned long long now = globaltimer_ns();
+                if (t0 == 0) t0 = now;
+                else expired = now - t0 > a.timeout_ns;
+            }
+        }
+        if (__any_sync(FULL, expired)) { ok = got; break; }
     }
 
     // ---- add: strictly left to right over v = 0 .. V-1, handed lane to lane

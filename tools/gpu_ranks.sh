@@ -13,8 +13,8 @@ run 29511 tests/multigpu/peer_comm_ranks.py > $out/${tag}_ranks_n${n}.log 2>&1
 echo "ranks_exit=$?" >> $out/${tag}_ranks_n${n}.log
 run 29512 bench.py --gpus "$n" > $out/${tag}_bench_n${n}.json 2> $out/${tag}_bench_n${n}.err
 echo "bench_exit=$?" >> $out/${tag}_bench_n${n}.err
-# the same collective driven from plain C++ (no Python, no NCCL), at every world size up to n
+# the same collective driven from plain C++ (no Python, no NCCL), at world 1 and n
 g++ -std=c++17 -O2 -Iinclude tests/multigpu/peer_comm_c.cpp -o /tmp/peer_comm_c -Lbase_b200 -lb9_groundwork \
     -Loracle -lb9_groundwork_ref -Wl,-rpath,$PWD/base_b200:$PWD/oracle &&
-for w in 1 2 4 8; do [ $w -le $n ] && timeout 120 /tmp/peer_comm_c $w; done > $out/${tag}_cpp_driver_n${n}.log 2>&1
+for w in 1 $n; do timeout 120 /tmp/peer_comm_c $w; done > $out/${tag}_cpp_driver_n${n}.log 2>&1
 tail -4 $out/${tag}_ranks_n${n}.log; cat $out/${tag}_cpp_driver_n${n}.log; cat $out/${tag}_bench_n${n}.json; tail -3 $out/${tag}_bench_n${n}.err

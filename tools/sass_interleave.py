@@ -37,8 +37,10 @@ def fast_path_runs(lib: str | Path, kernel_substr: str) -> list[tuple[str, int]]
             body.append(m.group(1).strip())
     if not name or kernel_substr not in name:
         raise LookupError(f"no kernel matching {kernel_substr!r} in {lib}")
-    i = next(j for j, t in enumerate(body) if t.startswith("VOTE.ALL"))
-    j = next(j for j in range(i + 2, len(body)) if body[j].startswith("BRA"))
+    # the fast path starts at the first DFMA that rounds with 1.5 * 2^52, just behind the vote
+    first = next(j for j, t in enumerate(body) if t.startswith("DFMA") and "6.75539944105574400000e+15" in t)
+    i = max(j for j in range(first) if body[j].startswith("VOTE.ALL"))
+    j = next(j for j in range(first, len(body)) if body[j].startswith("BRA"))
     runs: list[tuple[str, int]] = []
     for t in body[i:j]:
         m = re.match(r"DFMA (R\d+)", t)
