@@ -93,6 +93,31 @@ def main():
         assert (tiny["total"].view(np.int64) == tiny_alone.view(np.int64)).all()
         assert (tiny["total_fused"].view(np.int64) == tiny_alone.view(np.int64)).all(), f"rank {rank}: tiny fused"
         report["fused_step_us"] = round(step["us_fused_step"], 2)
+        # 3c. the fused step through caller-held tensors, replayed from a CUDA graph (the step
+        # counters live in device memory), mixed with two-launch steps on the same comm
+        per = V // world
+        lo_s, hi_s = vshards.local_star_range(rank, world, sn, V)
+        rows_t = torch.empty(sch, max(hi_s - lo_s, 1), dtype=torch.float64, device="cuda")
+        P_t = torch.empty(per, sch, dtype=torch.float64, device="cuda")
+        tot_t = torch.empty(sch, dtype=torch.float64, device="cuda")
+        work_t = torch.zeros(gw.lib().b9gw_lse_workspace_bytes(sch, per) // 4, dtype=torch.int32, device="cuda")
+        g2, s2 = torch.cuda.CUDAGraph(), torch.cuda.Stream()
+        s2.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s2):
+            comm.lse_generated_step(sn, sc, sch, rows_t, P_t, tot_t, work_t)
+            with torch.cuda.graph(g2, stream=s2):
+                comm.lse_generated_step(sn, sc, sch, rows_t, P_t, tot_t, work_t)
+                comm.lse_generated_step(sn, sc, sch, rows_t, P_t, tot_t, work_t)
+        torch.cuda.synchronize()
+        for _ in range(4):
+            tot_t.fill_(float("nan"))
+            torch.cuda.synchronize()
+            g2.replay()
+            torch.cuda.synchronize()
+            assert (bits(tot_t) == alone.view(np.int64)).all(), f"rank {rank}: fused graph replay"
+            assert (bits(comm.allreduce(P_t)) == alone.view(np.int64)).all()
+        comm.status()
+        report["fused_graph_replay_ok"] = True
         flat = gw.lse_generated(sch * sn, sc, local)["row_lse"].reshape(sch, sn)
         assert (ref.vshard_total(flat, V)[1].view(np.int64) == alone.view(np.int64)).all()
         report["sharded_step_bits_equal_world_1"] = True

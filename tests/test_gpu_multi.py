@@ -30,7 +30,7 @@ def test_peer_comm_ranks(built, world):
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     rep = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
     assert rep["bits_equal_checker"] and rep["graph_replay_ok"] and rep["missing_peer_reported"]
-    assert rep["sharded_step_bits_equal_world_1"]
+    assert rep["sharded_step_bits_equal_world_1"] and rep["fused_graph_replay_ok"]
     print(rep)
 
 
