@@ -21,6 +21,7 @@ COLS = [
     ("fp64_pipe_pct_of_active", "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"),
     ("fp64_pipe_pct_of_elapsed", "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_elapsed"),
     ("warp_inst_executed", "smsp__inst_executed.sum"),
+    ("fp64_inst_pct_of_peak_active", "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active"),
     ("dram_read_MB", "dram__bytes_read.sum"), ("dram_write_MB", "dram__bytes_write.sum"),
     ("dram_pct_of_peak", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"),
     ("smem_bank_conflicts", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum"),
