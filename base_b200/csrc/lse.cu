@@ -166,25 +166,45 @@ __device__ __forceinline__ double add_shards_in_order(const double (&pk)[B9GW_MA
     return acc;
 }
 
-// PEER: the cross-rank half of a fused step, run by the one warp per chain that knows the
-// chain's local shards are all pushed.  Polls this rank's own mailbox until the chain's V
-// packets show `step` (empty shards are known to hold +0 and are not waited for), adds them
-// left to right, stores total[chain] and moves the chain's step counter.  A peer that never
-// arrives costs the comm's timeout: NaN, sticky status — as in vshard.cu.
-__device__ void pull_and_total(const LseArgs &a, const PeerArgs &pa, long long chain, unsigned step,
-                               unsigned *tk, int lane) {
+// PEER: the cross-rank half of a fused step, run by the one warp per chain that took the
+// chain's last local ticket (so every local P[k] is in memory and acquired).  Lane l owns
+// shards l, l+32, ...: a local one it reads from partials[] and stores into every OTHER rank's
+// mailbox as a 16-byte self-flagging packet (vshard.cu); a remote one it polls for in this
+// rank's own mailbox; an empty one is known to be +0 and neither sent nor awaited.  Then the V
+// values are added left to right, total[chain] is stored and the chain's step counter moves.
+// The counter cannot move before this launch's pushes have been issued (same warp), nor can
+// a peer run ahead by more than a step (it needs our packets), so two mailbox parities are
+// enough — as in vshard.cu.  A peer that never arrives costs the comm's timeout: NaN and the
+// sticky status.
+__device__ void pull_and_total(const LseArgs &a, const PeerArgs &pa, long long chain, unsigned *tk, int lane) {
     const int V = 1 << a.vshift;
-    const uint4 *mine = pa.mail[pa.rank] + (size_t)(step & 1u) * V * (size_t)pa.max_chains + (size_t)chain;
+    const unsigned step = *(volatile unsigned *)(pa.seq + chain) + 1u;
+    const size_t parity_base = (size_t)(step & 1u) * V;
     double pk[B9GW_MAX_VSHARDS / 32];
     unsigned need = 0;
 #pragma unroll
     for (int q = 0; q < B9GW_MAX_VSHARDS / 32; ++q) {
         const int u = lane + 32 * q;
         pk[q] = 0.0;
-        if (u < V && shard_lo(a.n_total, a.vshift, u + 1) > shard_lo(a.n_total, a.vshift, u)) need |= 1u << q;
+        if (u >= V || shard_lo(a.n_total, a.vshift, u + 1) <= shard_lo(a.n_total, a.vshift, u)) continue;
+        if (u >= a.first_shard && u < a.first_shard + a.n_shards) {
+            pk[q] = __ldcg(a.partials + (long long)(u - a.first_shard) * a.chains + chain);
+            const unsigned lo = (unsigned)__double2loint(pk[q]), hi = (unsigned)__double2hiint(pk[q]);
+            const size_t slot = (parity_base + (size_t)u) * (size_t)pa.max_chains + (size_t)chain;
 #ifdef B9GW_DIAG
-        if ((a.diag & 1) && (u < a.first_shard || u >= a.first_shard + a.n_shards)) need &= ~(1u << q);
+            if (!(a.diag & 2))
 #endif
+            for (int d = 1; d < pa.world; ++d) {
+                int peer = pa.rank + d;
+                if (peer >= pa.world) peer -= pa.world;
+                b9gw::st_packet(pa.mail[peer] + slot, lo, hi, step);
+            }
+        } else {
+            need |= 1u << q;
+#ifdef B9GW_DIAG
+            if (a.diag & 1) need &= ~(1u << q);
+#endif
+        }
     }
 #ifdef B9GW_DIAG
     if (lane == 0 && chain < 16) g_diag[DIAG_SLOT(step, chain)] = b9gw::globaltimer_ns();
@@ -192,6 +212,7 @@ __device__ void pull_and_total(const LseArgs &a, const PeerArgs &pa, long long c
     // The warp stays converged: it leaves the loop as a whole, on a vote.  (Lanes leaving one by
     // one made everything after the loop — 128 shuffles — run ~12x slower on the rank that had
     // to wait: profiles/r03_groundwork.md.)
+    const uint4 *mine = pa.mail[pa.rank] + parity_base * (size_t)pa.max_chains + (size_t)chain;
     bool ok = true;
     unsigned long long t0 = *(volatile int *)pa.status ? ~0ULL : 0;   // a comm that timed out stays out of step
     for (;;) {
@@ -234,11 +255,11 @@ __device__ void pull_and_total(const LseArgs &a, const PeerArgs &pa, long long c
 // stored — all of them by this warp's lane 0, which also takes the tickets, so a ticket
 // releases them.  The warp that completes a virtual shard adds that shard's row values; the
 // warp that completes the chain's last local shard finishes the chain: with all shards local
-// (and no peers) it adds the shards left to right; PEER, every completed shard is first
-// pushed to every rank's mailbox, and the finishing warp pulls all V from its own.  Which warp
+// (and no peers) it adds the shards left to right; PEER, it runs pull_and_total.  Which warp
 // that is does not change any bit.  tickets[chain][k] counts finished rows of local shard k,
 // tickets[chain][n_shards] finished shards; each is reset by its last user, ready for the
-// next launch on the stream.
+// next launch on the stream.  (PEER: pushing each P from the warp that completed it — three
+// more round trips on 64 warps' tails per chain — cost more than it gained; measured.)
 template <bool PEER>
 __device__ void finish_rows(const LseArgs &a, const PeerArgs &pa, long long chain, long long s0,
                             long long s1, int lane) {
@@ -250,15 +271,13 @@ __device__ void finish_rows(const LseArgs &a, const PeerArgs &pa, long long chai
     const unsigned nonempty = a.n_total < V ? (unsigned)a.n_local : (unsigned)a.n_shards;
     const bool totals = PEER || (a.n_shards == V && a.total);
     bool all_done = false;
-    unsigned long long completed = 0;      // bit i: the i-th shard this warp touched was completed by it
-    int touched = 0;                       // <= s1 - s0 <= 64 (every touched shard holds one of our stars)
-    const long long v_first = (((g0 + 1) << a.vshift) + a.n_total - 1) / a.n_total - 1;   // shard holding g0
-    for (long long v = v_first; v < a.first_shard + a.n_shards; ++v) {
+    for (long long v = (((g0 + 1) << a.vshift) + a.n_total - 1) / a.n_total - 1;    // shard holding g0
+         v < a.first_shard + a.n_shards; ++v) {
         const long long lo = shard_lo(a.n_total, a.vshift, v), hi = shard_lo(a.n_total, a.vshift, v + 1);
         if (lo >= g1) break;
         if (hi <= lo) continue;                            // empty shard (n_total < V)
         const unsigned mine = (unsigned)((hi < g1 ? hi : g1) - (lo > g0 ? lo : g0));
-        const int k = (int)(v - a.first_shard), i = touched++;
+        const int k = (int)(v - a.first_shard);
         unsigned done = 0;
         if (lane == 0) done = ticket_add(&tk[k], mine) + mine == (unsigned)(hi - lo);
         if (!__shfl_sync(FULL, done, 0)) continue;
@@ -266,7 +285,6 @@ __device__ void finish_rows(const LseArgs &a, const PeerArgs &pa, long long chai
         // loads below bypass L1 (ld.cg), so no further fence is needed (each fence here is a
         // round trip on the kernel's serial tail, ~1.5 us apiece measured)
         const double p = warp_ordered_sum(rows, lo - a.star0, hi - a.star0, lane);
-        completed |= 1ULL << i;
         done = 0;
         if (lane == 0) {
             a.partials[(long long)k * a.chains + chain] = p;
@@ -275,40 +293,9 @@ __device__ void finish_rows(const LseArgs &a, const PeerArgs &pa, long long chai
         }
         all_done |= __shfl_sync(FULL, done, 0) != 0;
     }
-    unsigned step = 0;
-    if constexpr (PEER) {
-        // The completed shards' P are pushed after the warp's last ticket.  Nothing needs them
-        // earlier — the finishing warp polls for them like for any peer's — and the chain's
-        // counter cannot move before every push of this launch has landed, because moving it
-        // waits for all V packets.  (Measured alternatives, profiles/r03_groundwork.md: pushing
-        // inside the loop, and fetching the counter when the warp starts, were both slower.)
-        // Lane d stores into rank (rank + 1 + d)'s mailbox: remote peers first, self last.
-        if (completed) {
-            __syncwarp();                                  // lane 0's partials[] stores, read below by all
-            step = *(volatile unsigned *)(pa.seq + chain) + 1u;
-            int i = 0;
-            for (long long v = v_first; i < touched && completed >> i; ++v) {
-                if (shard_lo(a.n_total, a.vshift, v + 1) <= shard_lo(a.n_total, a.vshift, v)) continue;
-                if (completed >> i++ & 1ULL) {
-                    const double p = a.partials[(v - a.first_shard) * a.chains + chain];
-                    bool push = lane < pa.world;
-#ifdef B9GW_DIAG
-                    if (a.diag & 2) push = lane == pa.world - 1;   // self only
-#endif
-                    if (push) {
-                        int peer = pa.rank + 1 + lane;
-                        if (peer >= pa.world) peer -= pa.world;
-                        b9gw::st_packet(pa.mail[peer] + ((size_t)(step & 1u) * V + (size_t)v) * (size_t)pa.max_chains
-                                            + (size_t)chain,
-                                        (unsigned)__double2loint(p), (unsigned)__double2hiint(p), step);
-                    }
-                }
-            }
-        }
-    }
     if (!all_done) return;
     if constexpr (PEER) {
-        pull_and_total(a, pa, chain, step, tk, lane);
+        pull_and_total(a, pa, chain, tk, lane);
     } else {
         double pk[B9GW_MAX_VSHARDS / 32];
 #pragma unroll
@@ -364,8 +351,7 @@ lse_staged_kernel(const __grid_constant__ ExpConstants K, const __grid_constant_
     if (blockIdx.x == 0 && warp == 0 && a.n_total < (1LL << a.vshift)) {
         zero_empty_shards(a, chain, lane);
         if (PEER && a.n_local == 0)        // nothing local to finish: this warp does the cross-rank half
-            pull_and_total(a, pa, chain, *(volatile unsigned *)(pa.seq + chain) + 1u,
-                           a.tickets + chain * (a.n_shards + 1), lane);
+            pull_and_total(a, pa, chain, a.tickets + chain * (a.n_shards + 1), lane);
     }
 
     for (long long s = s0; s < s1; ++s) {
@@ -436,8 +422,7 @@ lse_stream_kernel(const __grid_constant__ LseArgs a, const __grid_constant__ Pee
     if (blockIdx.x == 0 && warp == 0 && a.n_total < (1LL << a.vshift)) {
         zero_empty_shards(a, chain, lane);
         if (PEER && a.n_local == 0)
-            pull_and_total(a, pa, chain, *(volatile unsigned *)(pa.seq + chain) + 1u,
-                           a.tickets + chain * (a.n_shards + 1), lane);
+            pull_and_total(a, pa, chain, a.tickets + chain * (a.n_shards + 1), lane);
     }
     if (s >= a.n_local) return;
     auto lse = [&](auto src) -> double {
