@@ -56,7 +56,7 @@ constexpr int CTA_THREADS = 256;
 // Without a minimum-CTAs launch bound ptxas schedules for full occupancy (32 registers a
 // thread) and un-interleaves the four exps of pass 2 into 1 + 1 + 2 dependent chains; shared
 // memory allows 6 CTAs per SM anyway.  With the bound it keeps all four chains interleaved
-// (62 registers): 304 instead of 330 us at 160 000 x 1024 (gpurun A/B, profiles/r03_*).
+// (62 registers): 304 instead of 330 us at 160 000 x 1024 (gpurun A/B, profiles/r02b_*).
 // The fused (PEER) instantiation carries the mailbox tail as well and spills at 64 registers;
 // it is bounded by the 6 CTAs shared memory allows at 1024 columns.
 #ifndef B9GW_STAGED_MIN_CTAS
@@ -211,7 +211,7 @@ __device__ void pull_and_total(const LseArgs &a, const PeerArgs &pa, long long c
 #endif
     // The warp stays converged: it leaves the loop as a whole, on a vote.  (Lanes leaving one by
     // one made everything after the loop — 128 shuffles — run ~12x slower on the rank that had
-    // to wait: profiles/r03_groundwork.md.)
+    // to wait: profiles/r02b_groundwork.md.)
     const uint4 *mine = pa.mail[pa.rank] + parity_base * (size_t)pa.max_chains + (size_t)chain;
     bool ok = true;
     unsigned long long t0 = *(volatile int *)pa.status ? ~0ULL : 0;   // a comm that timed out stays out of step

@@ -99,7 +99,7 @@ vshard_step_kernel(const StepArgs a) {
     }
     // The warp polls as a whole and leaves the loop on a vote, so that it is still converged
     // for the shuffles below (lanes leaving one by one made everything behind a poll loop run
-    // an order of magnitude slower in the fused kernel: profiles/r03_groundwork.md).
+    // an order of magnitude slower in the fused kernel: profiles/r02b_groundwork.md).
     bool got = !active;
     for (;;) {
         if (!got) {

@@ -95,7 +95,7 @@ def test_product_package_never_touches_the_checker():
 def test_pass2_exp_chains_stay_interleaved_in_the_sass(built, kernel):
     """The four exps a lane evaluates per pass-2 iteration must be interleaved in the SASS (one
     dependent DFMA chain per warp cannot feed the FP64 pipe); ptxas once serialised them after an
-    unrelated change, costing 5-9 % (profiles/r03_groundwork.md).  No DFMA may be followed by more
+    unrelated change, costing 5-9 % (profiles/r02b_groundwork.md).  No DFMA may be followed by more
     than one DFMA writing the same register, and all four chains' Horner steps must be present."""
     import sys
     sys.path.insert(0, str(ROOT / "tools"))

@@ -1,9 +1,9 @@
 #!/usr/bin/env bash
 # One gpurun call on ONE GPU: GPU tests, bench line, ncu launch list, ncu --set full of the
 # LSE kernels (memory-fed and register-fed) and the world-1 step kernel.
-# Usage (from the repo root on the GPU box): bash tools/gpu_round.sh r03
+# Usage (from the repo root on the GPU box): bash tools/gpu_round.sh r02b
 set -u
-tag=${1:-r03}
+tag=${1:-r02b}
 out=gpurun_out
 mkdir -p $out
 nvidia-smi --query-gpu=name,driver_version,clocks.max.sm,clocks.max.mem,power.limit --format=csv > $out/${tag}_gpu.csv

@@ -8,7 +8,7 @@ dependent DFMAs at ~10 clk dependent-issue latency, so the four chains must be I
 the instruction stream: with 6 warps per scheduler, one chain per warp keeps the FP64 pipe
 ~87 % fed, four keep it full (profiles/r02_groundwork.md "chains in flight").  The PTX is
 interleaved as written; whether the SASS stays interleaved is ptxas's decision and changed
-once without any change to the loop (a launch bound decided it, profiles/r03_groundwork.md).
+once without any change to the loop (a launch bound decided it, profiles/r02b_groundwork.md).
 This prints, per kernel, the destination registers of the fast path's DFMAs as runs; a run
 `Rn x11` is one exp executed on its own.
 """
