@@ -173,8 +173,8 @@ def _sharded_step(gw, comm, rank: int, world: int, local: int, warmup: int, step
     """Star sharding with real work per rank (still NOT a likelihood: the synthetic generator).
     A fixed job — 10 000 stars x 1024 terms x `chains` chains — is cut into the 64 virtual shards;
     each rank runs the fixed-order log-sum-exp of its own 64/W shards and then the cross-rank sum —
-    as two launches, and as ONE kernel with the sum fused into the LSE kernel's tail (packets pushed
-    by the warp that completes a shard).  Strong scaling: the job does not grow with W.  The total's bits are
+    as two launches, and as ONE kernel with the sum fused into the LSE kernel's tail (the warp that
+    finishes a chain locally pushes its shards to the peers and pulls theirs).  Strong scaling: the job does not grow with W.  The total's bits are
     asserted equal, on every rank, to those the rank gets alone from all 64 shards."""
     import numpy as np
     import torch

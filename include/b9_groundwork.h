@@ -313,12 +313,15 @@ int b9gw_allreduce_latency(b9gw_comm *comm, long long chains, int warmup,
 /*
  * The star-sharded step as ONE kernel: b9gw_lse_generated_shards over this
  * rank's V/world shards of the job, with the cross-rank sum fused into its tail.
- * The warp that completes a local shard stores that shard's P straight into
- * every rank's mailbox (the same 16-byte self-flagging packets as above); the
- * warp that completes a chain's last local shard then polls the chain's V slots
- * in its own mailbox and adds them left to right into total_dev[chain] — while
- * other chains' rows are still being evaluated on the rest of the GPU.  A rank
- * whose shards hold no star at all still takes part (it only pulls).  Same
+ * Only the warp that completes a chain's last local shard talks to the peers:
+ * it stores the chain's local P[] straight into every OTHER rank's mailbox (the
+ * same 16-byte self-flagging packets as above), polls its own mailbox for the
+ * remote shards and adds all V left to right into total_dev[chain] — while
+ * other chains' rows are still being evaluated on the rest of the GPU.  (A
+ * polling warp keeps its CTA resident; progress relies on the hardware issuing
+ * a grid's CTAs in block-index order on every rank, as every stream-K style
+ * kernel does.)  A rank whose shards hold no star at all still takes part (it
+ * only pulls).  Same
  * buffers, limits and workspace as b9gw_lse_generated_shards (the local shard
  * range is the comm's); same ordering rules, step counters, timeout behaviour
  * and bits as b9gw_ordered_allreduce, with which it may be freely mixed on one
