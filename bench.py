@@ -38,7 +38,7 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
-from base_b200 import staging  # noqa: E402
+from base_b200 import roofline, staging  # noqa: E402
 
 
 def _baseline_metric() -> str:
@@ -300,7 +300,9 @@ def main() -> int:
         launches += n
     clocks = cs.summary()
 
-    mhz = gw.device_info(local)["sm_clock_mhz"]
+    info = gw.device_info(local)
+    mhz = info["sm_clock_mhz"]
+    sm_mhz = clocks["sm_mhz"] if clocks else float(mhz)   # median SM clock sampled under load
 
     def lse_line(rows, res, reads_matrix):
         sec = res["ms_per_launch"] * 1e-3
@@ -309,6 +311,14 @@ def main() -> int:
              "frac_of_exp_spread_rate": round(rows * cols / sec * 1e-9 / rates["exp_spread"], 3)}
         if reads_matrix:
             d["algorithmic_gb_per_s"] = round(rows * cols * 8 / sec * 1e-9, 1)
+        else:
+            # the kernel's own bound: its instruction mix (from the committed ncu capture of this
+            # source) through the issue model, at the clock this run sampled
+            k = roofline.LSE_STAGED_INSTR_PER_32_TERMS
+            r_ = roofline.fp64_issue_roofline(rows * cols, sec, k["fp64"] / 32, k["other"] / 32,
+                                              info["sm_count"], sm_mhz, "terms/s")
+            d["frac_of_issue_bound"] = round(r_["frac"], 3)
+            d["issue_bound_gterms_per_s"] = round(r_["peak"] * 1e-9, 1)
         return d
 
     g = {
@@ -317,7 +327,7 @@ def main() -> int:
         "dfma_tflops_by_warps_per_sm": occ,
         # 2 chains in flight per scheduler: warp-DFMAs per cycle per scheduler = 2 / latency
         "fp64_dependent_issue_latency_clk": round(
-            2.0 / (l1["tflops"] * 1e12 / 2 / 32 / (gw.device_info(local)["sm_count"] * 4) / (mhz * 1e6)), 1),
+            2.0 / (l1["tflops"] * 1e12 / 2 / 32 / (info["sm_count"] * 4) / (mhz * 1e6)), 1),
         "dfma_rate_with_integer_company_per_dfma": company,
         "issue_model": "a DFMA holds a scheduler's issue port 2 cycles, any other instruction 1: "
                        "cycles ~ 2*n_fp64 + n_other (fits every ncu capture in profiles/r02_groundwork.md)",
@@ -336,9 +346,12 @@ def main() -> int:
         dist.destroy_process_group()
 
     line.update({"groundwork": g, "gpu_launches": launches, "clocks": clocks})
+    broken = roofline.check_line(line)                   # the driver's contract, checked before it is
+    if broken:
+        line["contract_violations"] = broken
     if rank == 0:
         print(json.dumps(line))
-    return 0
+    return 1 if broken else 0
 
 
 if __name__ == "__main__":
