@@ -103,3 +103,44 @@ def test_pass2_exp_chains_stay_interleaved_in_the_sass(built, kernel):
     runs = fast_path_runs(built.CUDA_LIB, kernel)
     assert sum(n for _, n in runs) == 4 * 14, runs          # 14 DFMAs per exp (rounding fma .. last Horner step)
     assert max(n for _, n in runs) <= 2, runs
+
+
+def _resource_usage(lib):
+    """{mangled kernel name: {"REG": n, "STACK": n, "SHARED": n, "LOCAL": n}} from cuobjdump -res-usage."""
+    import re
+    import subprocess
+    text = subprocess.run(["cuobjdump", "-res-usage", str(lib)], capture_output=True, text=True, check=True).stdout
+    out, name = {}, None
+    for line in text.splitlines():
+        m = re.match(r"\s*Function (\S+):", line)
+        if m:
+            name = m.group(1)
+        elif name and "REG:" in line:
+            out[name] = {k: int(v) for k, v in re.findall(r"(REG|STACK|SHARED|LOCAL):(\d+)", line)}
+            name = None
+    return out
+
+
+def test_kernels_fit_the_occupancy_their_launch_shapes_assume(built):
+    """Register and stack budgets read from the built library on the CPU box, so a compiler or source
+    change that spills, or that no longer fits the CTAs per SM the launch code counts on, fails here
+    and not as a slower (or unlaunchable) kernel on the GPU.  65 536 registers per SM."""
+    res = _resource_usage(built.CUDA_LIB)
+    staged = {k: v for k, v in res.items() if "lse_staged_kernel" in k}
+    assert len(staged) >= 3
+    for name, r in staged.items():
+        assert r["STACK"] == 0 and r["LOCAL"] == 0, (name, r)           # nothing spilled
+        peer = "ELb1E" in name
+        ctas = 6 if peer else 8                                         # __launch_bounds__(128, 8 | 6) in lse.cu
+        assert r["REG"] * 128 * ctas <= 65536, (name, r)
+    steps = {k: v for k, v in res.items() if "vshard_step_kernel" in k}
+    assert len(steps) == 6                                              # V = 4 .. 128
+    for name, r in steps.items():
+        assert r["REG"] * 256 <= 65536, (name, r)                       # one 256-thread CTA must launch
+        if "ILi32E" not in name and "ILi8E" not in name:                # V = 128 keeps 32 packets + 32 values per lane
+            assert r["STACK"] == 0, (name, r)
+    v64 = next(v for k, v in steps.items() if "ILi16E" in k)            # the default V = 64
+    assert v64["STACK"] == 0 and v64["REG"] <= 168                      # >= 1 CTA of 256 threads with room to spare
+    for name, r in res.items():
+        if "dfma_peak_kernel" in name or "rate_kernel" in name:
+            assert r["STACK"] == 0 and r["REG"] * 256 * 4 <= 65536, (name, r)   # >= 32 warps per SM: 0.99 of peak at ILP 8
