@@ -66,6 +66,43 @@ def hbm_roofline(algorithmic_bytes: float, seconds: float, peak_gbs: float, traf
             "frac": achieved / peak_gbs, "traffic": traffic}
 
 
+# ------------------------------------------------------------------ what batching buys
+
+# One launch of the stand-in kernel (fixed-order log-sum-exp, 1024 terms per row, terms produced on
+# chip) against the rows it covers: profiles/r02b_lse_sizes.log.  NOT a likelihood; it stands for
+# "a kernel that does ~1000 grid points of FP64 work per star" when sizing batches.
+LSE_LAUNCH_US = [(0, 8.4), (1250, 12.09), (2500, 14.49), (5000, 18.65), (10_000, 29.11),
+                 (20_000, 47.77), (40_000, 85.29), (160_000, 304.31)]
+HOST_ROUND_TRIP_US = 14.2      # launch + 8-byte D2H + sync of one dependent step (profiles/r02_groundwork.md)
+
+
+def launch_us(rows: float) -> float:
+    """Piecewise-linear read of LSE_LAUNCH_US; beyond the table the last slope continues."""
+    if rows < 0:
+        raise ValueError("rows cannot be negative")
+    t = LSE_LAUNCH_US
+    for (r0, u0), (r1, u1) in zip(t, t[1:]):
+        if rows <= r1:
+            return u0 + (u1 - u0) * (rows - r0) / (r1 - r0)
+    (r0, u0), (r1, u1) = t[-2], t[-1]
+    return u1 + (u1 - u0) / (r1 - r0) * (rows - r1)
+
+
+def speculative_steps_per_s(stars: int, depth: int, acceptance: float, chains: int = 1,
+                            host_us: float = HOST_ROUND_TRIP_US) -> float:
+    """Chain-steps per second of include/b9_spec_chain.hpp's rounds on one GPU, if a proposal cost
+    what `stars` rows of the stand-in kernel cost: a round evaluates depth x chains candidates in
+    one launch plus one host round trip, and completes (1 - (1-a)^depth) / a steps per chain."""
+    if stars < 1 or depth < 1 or chains < 1 or not 0.0 < acceptance <= 1.0:
+        raise ValueError("need stars, depth, chains >= 1 and 0 < acceptance <= 1")
+    steps = chains * (1.0 - (1.0 - acceptance) ** depth) / acceptance
+    return steps / (launch_us(stars * depth * chains) + host_us) * 1e6
+
+
+def best_depth(stars: int, acceptance: float, chains: int = 1, max_depth: int = 64) -> int:
+    return max(range(1, max_depth + 1), key=lambda k: speculative_steps_per_s(stars, k, acceptance, chains))
+
+
 # ------------------------------------------------------------------ the bench line
 
 _NUM = (int, float)

@@ -5,10 +5,11 @@
 // about BASE-9's sampler — not its proposal, its acceptance rule, its adaptation nor how many
 // random draws a step consumes — and does not imitate it.  It answers the one question about
 // the chain driver that can be answered without the source ("same-seed
-// accepted-chain parity with batched proposals"): a GPU evaluates one proposal in ~30 us and
-// sixteen in ~35 us, but a Metropolis chain is sequential.  How can a driver evaluate many
-// proposals per launch and still produce, for the same seed, exactly the chain the sequential
-// driver produces?
+// accepted-chain parity with batched proposals"): a launch costs ~9 us before it does any work
+// and a dependent host round trip another ~14 us, so a small cluster — or a big one sharded over
+// 8 GPUs — leaves the device idle unless several proposals, and several chains, share a launch;
+// but a Metropolis chain is sequential.  How can a driver evaluate many proposals per launch and
+// still produce, for the same seed, exactly the chain the sequential driver produces?
 //
 // By never letting the batch decide anything.  The caller hands over
 //   Ctx    everything a step reads or writes: current parameters and their log-posterior, the
@@ -34,7 +35,10 @@
 // guess costs evaluations, never correctness.  The guess "rejected" is right for the fraction
 // (1 - a) of steps at acceptance rate a, so a round of depth K completes (1 - (1-a)^K) / a
 // steps on average — about 3.5 per launch at a = 0.28, K = 16 (tests/cpp/spec_chain_test.cpp
-// measures 3.53), with C independent chains C times that per launch.
+// measures 3.53), with C independent chains C times that per launch.  Whether depth pays depends on
+// what a proposal costs: base_b200/roofline.py:speculative_steps_per_s puts the rounds on the
+// measured launch curve — about 3.4x at 100 stars, 2.3x at 1 250 (depth 6), 1.2x at 10 000 stars on
+// one GPU (depth 3; depth 16 loses) — and independent chains pay until the launch is throughput-bound.
 //
 // Requirement on `batch`: the value for a parameter vector must not depend on what else is in
 // the batch nor on the batch's size — which is what fixed-order reductions buy (lse.cu, vshard.cu).

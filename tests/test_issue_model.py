@@ -91,6 +91,29 @@ def test_rooflines_reject_nonsense():
     assert h["bound"] == "hbm" and h["frac"] == pytest.approx(2416.5 / 6552.6, rel=1e-3)
 
 
+def test_what_batching_buys_on_the_measured_launch_curve():
+    """Speculative depth pays where one proposal is a latency-bound launch, not on a 10 000-star
+    cluster on one GPU; independent chains pay until the launch reaches the throughput bound."""
+    assert rf.launch_us(10_000) == pytest.approx(29.11) and rf.launch_us(160_000) == pytest.approx(304.31)
+    assert rf.launch_us(7_500) == pytest.approx((18.65 + 29.11) / 2)
+    a = 0.25
+    one = {s: rf.speculative_steps_per_s(s, 1, a) for s in (100, 1_250, 10_000)}
+    assert one[10_000] == pytest.approx(1e6 / (29.11 + 14.2))
+    # 10 000 stars: the launch is already most of a wave; depth buys < 25 %, and deep speculation loses
+    assert rf.speculative_steps_per_s(10_000, rf.best_depth(10_000, a), a) < 1.25 * one[10_000]
+    assert rf.speculative_steps_per_s(10_000, 16, a) < one[10_000]
+    assert rf.best_depth(10_000, a) <= 3
+    # 1 250 stars (a 10 000-star cluster sharded over 8 GPUs): about 2.3x at depth 6
+    assert 2.0 < rf.speculative_steps_per_s(1_250, rf.best_depth(1_250, a), a) / one[1_250] < 2.6
+    assert 4 <= rf.best_depth(1_250, a) <= 8
+    # 100 stars (cfg1): the launch is all latency, depth 16 gives > 3x
+    assert rf.speculative_steps_per_s(100, 16, a) > 3.0 * one[100] and rf.best_depth(100, a) >= 8
+    # independent chains: 64 chains of 100 stars in one launch, > 30x one chain
+    assert rf.speculative_steps_per_s(100, 1, a, chains=64) > 30 * one[100]
+    with pytest.raises(ValueError):
+        rf.speculative_steps_per_s(100, 0, a)
+
+
 # ------------------------------------------------------------------ the bench line
 
 BLOCKED = {
